@@ -39,6 +39,12 @@ extern "C" {
 
 #define PW_ABI_VERSION 1
 
+#if defined(__GNUC__)
+#define PW_API __attribute__((visibility("default")))
+#else
+#define PW_API
+#endif
+
 /* limits of the table format */
 #define PW_MAX_OBJECTS 32 /* movables incl. the agent (benchmark max: 19) */
 #define PW_MAX_WIDTH 64   /* grid columns incl. the wall border (benchmark max: 47) */
@@ -94,33 +100,33 @@ typedef struct PwEngine PwEngine;
  * sorted descending, goals pull their movables to the front.  Writes at most `cap` bytes
  * to `out` and the needed size to `*size` (call with out=NULL to query).  Replaces the
  * 86 s Python table build of the reference. */
-int pw_compile_puzzle(const char* text, size_t text_len, void* out, size_t cap, size_t* size);
+PW_API int pw_compile_puzzle(const char* text, size_t text_len, void* out, size_t cap, size_t* size);
 
 /* Creates an engine on CUDA device `device` from `num_puzzles` concatenated table blobs.
  * offsets_u64[p] = start of puzzle p inside `blob` (u64 units).  `blob` is HOST memory
  * and is copied.  Replaces: constructing PushWorldPuzzle objects (gym_env.py:66-69). */
-int pw_engine_create(const void* blob, size_t blob_bytes, const uint32_t* offsets_u64,
+PW_API int pw_engine_create(const void* blob, size_t blob_bytes, const uint32_t* offsets_u64,
                      int num_puzzles, int device, PwEngine** out);
-int pw_engine_destroy(PwEngine* engine);
+PW_API int pw_engine_destroy(PwEngine* engine);
 
 /* Static facts: number of puzzles, max objects over all puzzles (= number of x/y planes
  * a state tensor must have), max width / height in cells. */
-int pw_engine_info(const PwEngine* engine, int* num_puzzles, int* n_max, int* max_width,
+PW_API int pw_engine_info(const PwEngine* engine, int* num_puzzles, int* n_max, int* max_width,
                    int* max_height);
 
 /* Copies the engine's device-side status block to host: status[0] = number of invalid
  * actions seen since the last poll (then cleared).  SYNCHRONISES `stream`. */
-int pw_engine_poll(PwEngine* engine, uint64_t status[4], void* stream);
+PW_API int pw_engine_poll(PwEngine* engine, uint64_t status[4], void* stream);
 
 /* Thread-local description of the last error on this thread ("" if none). */
-const char* pw_last_error(void);
-int pw_abi_version(void);
+PW_API const char* pw_last_error(void);
+PW_API int pw_abi_version(void);
 
 /* x/y <- initial_state of each environment's puzzle; steps <- 0 (nullable).
  * Replaces: PushWorldEnv.reset's state assignment (gym_env.py:171-176).  Planes
  * j >= n_objects(puzzle) are zero-filled.  If `reset_mask` (uint8[N]) is non-NULL only
  * environments with a non-zero mask are reset. */
-int pw_reset(PwEngine* engine, int64_t n_envs, const int32_t* puzzle_id, int puzzle_uniform,
+PW_API int pw_reset(PwEngine* engine, int64_t n_envs, const int32_t* puzzle_id, int puzzle_uniform,
              int32_t* x, int32_t* y, int64_t stride, int32_t* steps, const uint8_t* reset_mask,
              void* stream);
 
@@ -135,7 +141,7 @@ int pw_reset(PwEngine* engine, int64_t n_envs, const int32_t* puzzle_id, int puz
  *   moved[N]       uint32 bit j = object j changed position, 0 if the move was blocked;
  *                  mirrors RelativeState.moved_object_indices (cpp/src/pushworld_puzzle.cc:439-452) (nullable)
  */
-int pw_step(PwEngine* engine, int64_t n_envs, const int32_t* puzzle_id, int puzzle_uniform,
+PW_API int pw_step(PwEngine* engine, int64_t n_envs, const int32_t* puzzle_id, int puzzle_uniform,
             int32_t* x, int32_t* y, int64_t stride, const uint8_t* action, float* reward,
             int8_t* dgoals, uint8_t* terminated, uint8_t* truncated, int32_t* steps,
             int32_t max_steps, uint32_t* moved, void* stream);
@@ -152,7 +158,7 @@ int pw_step(PwEngine* engine, int64_t n_envs, const int32_t* puzzle_id, int puzz
  *               steps in which anything moved, sum of max(delta_goals,0)}; this is the
  *               vector the multi-GPU driver all-reduces (nullable)
  */
-int pw_rollout(PwEngine* engine, int64_t n_envs, int32_t n_steps, const int32_t* puzzle_id,
+PW_API int pw_rollout(PwEngine* engine, int64_t n_envs, int32_t n_steps, const int32_t* puzzle_id,
                int puzzle_uniform, int32_t* x, int32_t* y, int64_t stride,
                const uint8_t* actions, float* reward, int8_t* dgoals, uint8_t* terminated,
                uint8_t* truncated, int32_t* steps, int32_t max_steps, float* return_sum,
@@ -165,7 +171,7 @@ int pw_rollout(PwEngine* engine, int64_t n_envs, int32_t n_steps, const int32_t*
  *   moved[4N] uint32 moved-object bitmask (RelativeState.moved_object_indices)
  *   goal[4N]  uint8  satisfiesGoal(successor)                           (both nullable)
  */
-int pw_expand(PwEngine* engine, int64_t n_states, const int32_t* puzzle_id, int puzzle_uniform,
+PW_API int pw_expand(PwEngine* engine, int64_t n_states, const int32_t* puzzle_id, int puzzle_uniform,
               const int32_t* x_in, const int32_t* y_in, int64_t stride_in, int32_t* x_out,
               int32_t* y_out, int64_t stride_out, uint32_t* moved, uint8_t* goal, void* stream);
 
@@ -177,7 +183,7 @@ int pw_expand(PwEngine* engine, int64_t n_states, const int32_t* puzzle_id, int 
  *   top/left and zeros elsewhere.  pad_*_cells must be >= every rendered puzzle's dims.
  *   pixels_per_cell >= 1 + 2*border_width, border_width >= 1 (puzzle.py:444-448).
  */
-int pw_render(PwEngine* engine, int64_t n_envs, const int32_t* puzzle_id, int puzzle_uniform,
+PW_API int pw_render(PwEngine* engine, int64_t n_envs, const int32_t* puzzle_id, int puzzle_uniform,
               const int32_t* x, const int32_t* y, int64_t stride, void* out, int dtype,
               int pixels_per_cell, int border_width, int pad_h_cells, int pad_w_cells,
               void* stream);
@@ -185,7 +191,7 @@ int pw_render(PwEngine* engine, int64_t n_envs, const int32_t* puzzle_id, int pu
 /* pw_step and pw_render of the new state fused in one launch (BASELINE config 5):
  * what PushWorldEnv.step returns -- observation, reward, terminated, truncated
  * (gym_env.py:188-226). */
-int pw_step_render(PwEngine* engine, int64_t n_envs, const int32_t* puzzle_id,
+PW_API int pw_step_render(PwEngine* engine, int64_t n_envs, const int32_t* puzzle_id,
                    int puzzle_uniform, int32_t* x, int32_t* y, int64_t stride,
                    const uint8_t* action, float* reward, int8_t* dgoals, uint8_t* terminated,
                    uint8_t* truncated, int32_t* steps, int32_t max_steps, void* out, int dtype,

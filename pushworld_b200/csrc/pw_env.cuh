@@ -1,0 +1,201 @@
+// pw_env.cuh -- per-thread environment state policies for pw_core.cuh (device only).
+//
+// One CUDA thread owns one environment.  Two storage policies:
+//   RegEnv<NMAX>  positions, shape descriptors and goal positions live in registers;
+//                 every loop over objects is fully unrolled so no array is ever indexed
+//                 dynamically (the pusher index, the only runtime index, goes through a
+//                 select chain).  Used when the launch's puzzles have n <= NMAX (4 or 8).
+//   SmemEnv       positions live in shared memory, column `threadIdx.x` of an
+//                 [n_max][blockDim] int32 array per coordinate: a dynamic object index is
+//                 a different row of the same bank, so accesses are conflict free however
+//                 the lanes of a warp diverge.  Descriptors are read from the table.
+// The table view is either the block's shared-memory copy of a puzzle blob (all threads of
+// the launch share one puzzle) or the engine's global blob read through the read-only path.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "pw_core.cuh"
+
+namespace pw {
+
+struct SharedTable {
+  const uint64_t* base;
+  __device__ __forceinline__ uint64_t row(int off) const { return base[off]; }
+  __device__ __forceinline__ uint32_t word(int i) const {
+    return reinterpret_cast<const uint32_t*>(base)[i];
+  }
+};
+
+struct GlobalTable {
+  const uint64_t* base;
+  __device__ __forceinline__ uint64_t row(int off) const { return __ldg(base + off); }
+  __device__ __forceinline__ uint32_t word(int i) const {
+    return __ldg(reinterpret_cast<const uint32_t*>(base) + i);
+  }
+};
+
+template <class Table>
+struct EnvBase {
+  Table t;
+  int n_, g_, w_, h_, wall_off_, awall_off_, desc_word_;
+  __device__ __forceinline__ void init_header(Table table) {
+    t = table;
+    const uint32_t dims = t.word(kHdrDims), counts = t.word(kHdrCounts);
+    w_ = (int)(dims & 0xffffu);
+    h_ = (int)(dims >> 16);
+    n_ = (int)(counts & 0xffffu);
+    g_ = (int)(counts >> 16);
+    wall_off_ = (int)t.word(kHdrWallOff);
+    awall_off_ = (int)t.word(kHdrAwallOff);
+    desc_word_ = (int)t.word(kHdrObjOff) * 2;
+  }
+  __device__ __forceinline__ int n() const { return n_; }
+  __device__ __forceinline__ int g() const { return g_; }
+  __device__ __forceinline__ int width() const { return w_; }
+  __device__ __forceinline__ int height() const { return h_; }
+  __device__ __forceinline__ int wall_off() const { return wall_off_; }
+  __device__ __forceinline__ int awall_off() const { return awall_off_; }
+  __device__ __forceinline__ uint64_t row(int off) const { return t.row(off); }
+  __device__ __forceinline__ uint32_t table_desc(int j, int k) const {
+    return t.word(desc_word_ + 4 * j + k);
+  }
+};
+
+template <int NMAX, class Table>
+struct RegEnv : EnvBase<Table> {
+  static constexpr int kStaticN = NMAX;
+  static constexpr int kUnroll = NMAX;
+  int px[NMAX], py[NMAX];
+  uint32_t d[NMAX];
+  int gx[NMAX], gy[NMAX];  // goal of object k+1 at index k
+
+  __device__ __forceinline__ void init(Table table) {
+    this->init_header(table);
+#pragma unroll
+    for (int j = 0; j < NMAX; ++j) {
+      const bool live = j < this->n_;
+      d[j] = live ? this->table_desc(j, 0) : 0u;
+      const uint32_t goal = (live && j >= 1) ? this->table_desc(j, 2) : kNoGoal;
+      if (j >= 1) {
+        gx[j - 1] = lo16(goal);
+        gy[j - 1] = hi16(goal);
+      }
+      px[j] = 0;
+      py[j] = 0;
+    }
+    gx[NMAX - 1] = gy[NMAX - 1] = 0;
+  }
+  __device__ __forceinline__ void load(const int32_t* x, const int32_t* y, int64_t stride,
+                                       int64_t e) {
+#pragma unroll
+    for (int j = 0; j < NMAX; ++j)
+      if (j < this->n_) {
+        px[j] = x[j * stride + e];
+        py[j] = y[j * stride + e];
+      }
+  }
+  __device__ __forceinline__ void load_initial() {
+#pragma unroll
+    for (int j = 0; j < NMAX; ++j)
+      if (j < this->n_) {
+        const uint32_t v = this->table_desc(j, 1);
+        px[j] = lo16(v);
+        py[j] = hi16(v);
+      }
+  }
+  __device__ __forceinline__ void store(int32_t* x, int32_t* y, int64_t stride, int64_t e) const {
+#pragma unroll
+    for (int j = 0; j < NMAX; ++j)
+      if (j < this->n_) {
+        x[j * stride + e] = px[j];
+        y[j * stride + e] = py[j];
+      }
+  }
+  __device__ __forceinline__ uint32_t desc(int j) const { return d[j]; }
+  __device__ __forceinline__ int x(int j) const { return px[j]; }
+  __device__ __forceinline__ int y(int j) const { return py[j]; }
+  __device__ __forceinline__ int goal_x(int k) const { return gx[k]; }
+  __device__ __forceinline__ int goal_y(int k) const { return gy[k]; }
+  __device__ __forceinline__ uint32_t desc_dyn(int i) const {
+    uint32_t v = d[0];
+#pragma unroll
+    for (int k = 1; k < NMAX; ++k) v = (i == k) ? d[k] : v;
+    return v;
+  }
+  __device__ __forceinline__ int x_dyn(int i) const {
+    int v = px[0];
+#pragma unroll
+    for (int k = 1; k < NMAX; ++k) v = (i == k) ? px[k] : v;
+    return v;
+  }
+  __device__ __forceinline__ int y_dyn(int i) const {
+    int v = py[0];
+#pragma unroll
+    for (int k = 1; k < NMAX; ++k) v = (i == k) ? py[k] : v;
+    return v;
+  }
+  __device__ __forceinline__ void translate(uint32_t mask, int dx, int dy) {
+#pragma unroll
+    for (int j = 0; j < NMAX; ++j) {
+      const bool m = (mask >> j) & 1u;
+      px[j] += m ? dx : 0;
+      py[j] += m ? dy : 0;
+    }
+  }
+};
+
+template <class Table>
+struct SmemEnv : EnvBase<Table> {
+  static constexpr int kStaticN = 0;
+  static constexpr int kUnroll = 1;
+  int* sx;  // &s_x[threadIdx.x]; object j at sx[j * pitch]
+  int* sy;
+  int pitch;
+
+  // x_col / y_col: this thread's column; object j lives at x_col[j * col_pitch]
+  __device__ __forceinline__ void init(Table table, int* x_col, int* y_col, int col_pitch) {
+    this->init_header(table);
+    pitch = col_pitch;
+    sx = x_col;
+    sy = y_col;
+  }
+  __device__ __forceinline__ void load(const int32_t* x, const int32_t* y, int64_t stride,
+                                       int64_t e) {
+    for (int j = 0; j < this->n_; ++j) {
+      sx[j * pitch] = x[j * stride + e];
+      sy[j * pitch] = y[j * stride + e];
+    }
+  }
+  __device__ __forceinline__ void load_initial() {
+    for (int j = 0; j < this->n_; ++j) {
+      const uint32_t v = this->table_desc(j, 1);
+      sx[j * pitch] = lo16(v);
+      sy[j * pitch] = hi16(v);
+    }
+  }
+  __device__ __forceinline__ void store(int32_t* x, int32_t* y, int64_t stride, int64_t e) const {
+    for (int j = 0; j < this->n_; ++j) {
+      x[j * stride + e] = sx[j * pitch];
+      y[j * stride + e] = sy[j * pitch];
+    }
+  }
+  __device__ __forceinline__ uint32_t desc(int j) const { return this->table_desc(j, 0); }
+  __device__ __forceinline__ uint32_t desc_dyn(int j) const { return this->table_desc(j, 0); }
+  __device__ __forceinline__ int x(int j) const { return sx[j * pitch]; }
+  __device__ __forceinline__ int y(int j) const { return sy[j * pitch]; }
+  __device__ __forceinline__ int x_dyn(int j) const { return sx[j * pitch]; }
+  __device__ __forceinline__ int y_dyn(int j) const { return sy[j * pitch]; }
+  __device__ __forceinline__ int goal_x(int k) const { return lo16(this->table_desc(k + 1, 2)); }
+  __device__ __forceinline__ int goal_y(int k) const { return hi16(this->table_desc(k + 1, 2)); }
+  __device__ __forceinline__ void translate(uint32_t mask, int dx, int dy) {
+    while (mask) {
+      const int j = __ffs((int)mask) - 1;
+      mask &= mask - 1;
+      if (dx) sx[j * pitch] += dx;
+      if (dy) sy[j * pitch] += dy;
+    }
+  }
+};
+
+}  // namespace pw

@@ -1,0 +1,97 @@
+// pw_internal.h -- parameter blocks shared by the kernels and the C-ABI layer (not public).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pw {
+
+constexpr uint32_t kFlagAutoreset = 1u;
+
+struct StepParams {
+  const uint64_t* blob;        // all puzzle tables, device
+  const uint32_t* puzzle_off;  // u64 offset of each puzzle inside blob, device
+  int64_t N;
+  int32_t T;
+  const int32_t* puzzle_id;  // device int32[N] or nullptr
+  int32_t puzzle_uniform;
+  int32_t uniform_u64;  // blob size of puzzle_uniform (u64 units)
+  int32_t n_max;        // planes in x / y
+  int32_t* x;
+  int32_t* y;
+  int64_t stride;
+  const uint8_t* actions;  // [T][N]
+  float* reward;           // [T][N] or nullptr
+  int8_t* dgoals;
+  uint8_t* terminated;
+  uint8_t* truncated;
+  uint32_t* moved;
+  int32_t* steps;  // [N] in/out or nullptr
+  int32_t max_steps;
+  float* return_sum;             // [N] or nullptr
+  unsigned long long* counters;  // [4] or nullptr
+  unsigned long long* status;    // engine status block
+  uint32_t flags;
+};
+
+struct ExpandParams {
+  const uint64_t* blob;
+  const uint32_t* puzzle_off;
+  int64_t N;
+  const int32_t* puzzle_id;
+  int32_t puzzle_uniform;
+  int32_t uniform_u64;
+  int32_t n_max;
+  const int32_t* x_in;
+  const int32_t* y_in;
+  int64_t stride_in;
+  int32_t* x_out;
+  int32_t* y_out;
+  int64_t stride_out;
+  uint32_t* moved;
+  uint8_t* goal;
+};
+
+struct ResetParams {
+  const uint64_t* blob;
+  const uint32_t* puzzle_off;
+  int64_t N;
+  const int32_t* puzzle_id;
+  int32_t puzzle_uniform;
+  int32_t n_max;
+  int32_t* x;
+  int32_t* y;
+  int64_t stride;
+  int32_t* steps;
+  const uint8_t* reset_mask;
+};
+
+struct RenderParams {
+  const uint64_t* blob;
+  const uint32_t* puzzle_off;
+  int64_t N;
+  const int32_t* puzzle_id;
+  int32_t puzzle_uniform;
+  int32_t n_max;
+  const int32_t* x;
+  const int32_t* y;
+  int64_t stride;
+  void* out;
+  int32_t dtype;
+  int32_t ppc, bw;
+  int32_t out_h, out_w;  // pixels
+  int32_t max_cells;     // max width*height over the engine's puzzles
+  int32_t max_blob_u64;
+};
+
+cudaError_t upload_reward_lut(const float* host_lut);
+cudaError_t configure_kernels(size_t max_dynamic_smem);
+cudaError_t configure_render_kernels();
+// n_limit: max objects over the puzzles this launch can touch (selects the register policy)
+cudaError_t launch_steps(const StepParams& p, int n_limit, cudaStream_t stream);
+cudaError_t launch_expand(const ExpandParams& p, int n_limit, cudaStream_t stream);
+cudaError_t launch_reset(const ResetParams& p, cudaStream_t stream);
+cudaError_t launch_render(const RenderParams& p, const StepParams* fused_step, int n_limit,
+                          cudaStream_t stream);
+cudaError_t upload_palette(const uint8_t* rgb, const float* rgb_f32, int n_colors);
+
+}  // namespace pw

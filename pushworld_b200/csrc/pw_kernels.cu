@@ -1,0 +1,275 @@
+// pw_kernels.cu -- sm_100a kernels for the PushWorld dynamics path (step / rollout / expand /
+// reset) and their launchers.  One thread per environment; see pw_env.cuh for the two state
+// policies and pw_core.cuh for the transition rule.  DESIGN.md section 3 has the rationale and
+// the measured comparison against a warp-per-environment layout.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "pw_env.cuh"
+#include "pw_internal.h"
+#include "pw_steps.cuh"
+
+namespace pw {
+
+cudaError_t upload_reward_lut(const float* host_lut) {
+  return cudaMemcpyToSymbol(c_reward_lut, host_lut, sizeof(float) * (2 * kMaxObjects + 1));
+}
+
+namespace {
+
+constexpr int kBlock = 128;
+
+// Copies one puzzle blob into shared memory (all threads of the block take part).
+__device__ __forceinline__ void stage_table(uint64_t* dst, const uint64_t* src, int n_u64) {
+  for (int i = threadIdx.x; i < n_u64; i += blockDim.x) dst[i] = __ldg(src + i);
+  __syncthreads();
+}
+
+__device__ __forceinline__ uint32_t warp_sum(uint32_t v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------
+// T fused steps of one environment per thread (pw_steps.cuh) + block-level counter flush.
+// ------------------------------------------------------------------------------------------
+template <class Env>
+__device__ __forceinline__ void run_steps(Env& env, const StepParams& p, int64_t e, bool active,
+                                          uint32_t* s_counters) {
+  StepCounts c;
+  if (active) run_steps_thread(env, p, e, c);
+  if (p.counters || p.status) {
+    const uint32_t c_term = warp_sum(c.terminated), c_moved = warp_sum(c.moved);
+    const uint32_t c_dg = warp_sum(c.dgoals), c_invalid = warp_sum(c.invalid);
+    if ((threadIdx.x & 31) == 0) {
+      if (c_term) atomicAdd(&s_counters[0], c_term);
+      if (c_moved) atomicAdd(&s_counters[1], c_moved);
+      if (c_dg) atomicAdd(&s_counters[2], c_dg);
+      if (c_invalid) atomicAdd(&s_counters[3], c_invalid);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      if (p.counters) {
+        const int64_t first = (int64_t)blockIdx.x * blockDim.x;
+        const int64_t rest = p.N - first;
+        const int64_t live = rest < (int64_t)blockDim.x ? rest : (int64_t)blockDim.x;
+        atomicAdd(&p.counters[0], (unsigned long long)(live > 0 ? live : 0) * (unsigned long long)p.T);
+        if (s_counters[0]) atomicAdd(&p.counters[1], (unsigned long long)s_counters[0]);
+        if (s_counters[1]) atomicAdd(&p.counters[2], (unsigned long long)s_counters[1]);
+        if (s_counters[2]) atomicAdd(&p.counters[3], (unsigned long long)s_counters[2]);
+      }
+      if (p.status && s_counters[3]) atomicAdd(&p.status[0], (unsigned long long)s_counters[3]);
+    }
+  }
+}
+
+// All environments of the launch share puzzle `p.puzzle_uniform`: its table is staged in
+// shared memory once per block.
+template <int NMAX>
+__global__ void __launch_bounds__(kBlock) k_steps_uniform(const StepParams p) {
+  extern __shared__ uint64_t smem[];
+  __shared__ uint32_t s_counters[4];
+  if (threadIdx.x < 4) s_counters[threadIdx.x] = 0;
+  const uint64_t* src = p.blob + p.puzzle_off[p.puzzle_uniform];
+  stage_table(smem, src, p.uniform_u64);
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = e < p.N;
+  if constexpr (NMAX > 0) {
+    RegEnv<NMAX, SharedTable> env;
+    env.init(SharedTable{smem});
+    run_steps(env, p, e, active, s_counters);
+  } else {
+    SmemEnv<SharedTable> env;
+    int* st = reinterpret_cast<int*>(smem + p.uniform_u64);
+    env.init(SharedTable{smem}, st + threadIdx.x, st + p.n_max * kBlock + threadIdx.x, kBlock);
+    run_steps(env, p, e, active, s_counters);
+  }
+}
+
+// Per-environment puzzle ids: tables are read from global memory (L1/L2 resident, the whole
+// benchmark set is < 1 MB).
+template <int NMAX>
+__global__ void __launch_bounds__(kBlock) k_steps_mixed(const StepParams p) {
+  extern __shared__ uint64_t smem[];
+  __shared__ uint32_t s_counters[4];
+  if (threadIdx.x < 4) s_counters[threadIdx.x] = 0;
+  __syncthreads();
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = e < p.N;
+  const int pid = active ? p.puzzle_id[e] : 0;
+  const GlobalTable table{p.blob + p.puzzle_off[pid]};
+  if constexpr (NMAX > 0) {
+    RegEnv<NMAX, GlobalTable> env;
+    env.init(table);
+    run_steps(env, p, e, active, s_counters);
+  } else {
+    SmemEnv<GlobalTable> env;
+    int* st = reinterpret_cast<int*>(smem);
+    env.init(table, st + threadIdx.x, st + p.n_max * kBlock + threadIdx.x, kBlock);
+    run_steps(env, p, e, active, s_counters);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Successor expansion: 4 actions per state; a step is undone by translating the pushed set
+// back, so the state is loaded once.
+// ------------------------------------------------------------------------------------------
+template <class Env>
+__device__ __forceinline__ void run_expand(Env& env, const ExpandParams& p, int64_t e) {
+  env.load(p.x_in, p.y_in, p.stride_in, e);
+  const int g = env.g();
+#pragma unroll 1
+  for (int a = 0; a < 4; ++a) {
+    const uint32_t moved = step(env, a);
+    const int64_t s = (int64_t)a * p.N + e;
+    env.store(p.x_out, p.y_out, p.stride_out, s);
+    if (p.moved) p.moved[s] = moved;
+    if (p.goal) p.goal[s] = achieved_goals(env) == g ? 1 : 0;  // pushworld_puzzle.cc:462-469
+    env.translate(moved, -action_dx(a), -action_dy(a));
+  }
+}
+
+template <int NMAX>
+__global__ void __launch_bounds__(kBlock) k_expand_uniform(const ExpandParams p) {
+  extern __shared__ uint64_t smem[];
+  const uint64_t* src = p.blob + p.puzzle_off[p.puzzle_uniform];
+  stage_table(smem, src, p.uniform_u64);
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= p.N) return;
+  if constexpr (NMAX > 0) {
+    RegEnv<NMAX, SharedTable> env;
+    env.init(SharedTable{smem});
+    run_expand(env, p, e);
+  } else {
+    SmemEnv<SharedTable> env;
+    int* st = reinterpret_cast<int*>(smem + p.uniform_u64);
+    env.init(SharedTable{smem}, st + threadIdx.x, st + p.n_max * kBlock + threadIdx.x, kBlock);
+    run_expand(env, p, e);
+  }
+}
+
+template <int NMAX>
+__global__ void __launch_bounds__(kBlock) k_expand_mixed(const ExpandParams p) {
+  extern __shared__ uint64_t smem[];
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= p.N) return;
+  const GlobalTable table{p.blob + p.puzzle_off[p.puzzle_id[e]]};
+  if constexpr (NMAX > 0) {
+    RegEnv<NMAX, GlobalTable> env;
+    env.init(table);
+    run_expand(env, p, e);
+  } else {
+    SmemEnv<GlobalTable> env;
+    int* st = reinterpret_cast<int*>(smem);
+    env.init(table, st + threadIdx.x, st + p.n_max * kBlock + threadIdx.x, kBlock);
+    run_expand(env, p, e);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// reset: state <- initial_state (gym_env.py:171-176)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) k_reset(const ResetParams p) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= p.N) return;
+  if (p.reset_mask && p.reset_mask[e] == 0) return;
+  const int pid = p.puzzle_id ? p.puzzle_id[e] : p.puzzle_uniform;
+  const GlobalTable t{p.blob + p.puzzle_off[pid]};
+  const int n = (int)(t.word(kHdrCounts) & 0xffffu);
+  const int desc_word = (int)t.word(kHdrObjOff) * 2;
+  for (int j = 0; j < p.n_max; ++j) {
+    int vx = 0, vy = 0;
+    if (j < n) {
+      const uint32_t v = t.word(desc_word + 4 * j + 1);
+      vx = lo16(v);
+      vy = hi16(v);
+    }
+    p.x[j * p.stride + e] = vx;
+    p.y[j * p.stride + e] = vy;
+  }
+  if (p.steps) p.steps[e] = 0;
+}
+
+inline unsigned grid_for(int64_t n) { return (unsigned)((n + kBlock - 1) / kBlock); }
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------
+cudaError_t launch_steps(const StepParams& p, int n_limit, cudaStream_t stream) {
+  if (p.N == 0 || p.T == 0) return cudaSuccess;
+  const unsigned grid = grid_for(p.N);
+  const size_t state_bytes = (size_t)p.n_max * 2 * kBlock * sizeof(int);
+  if (p.puzzle_id == nullptr) {
+    const size_t tbl = (size_t)p.uniform_u64 * 8;
+    if (n_limit <= 4) {
+      k_steps_uniform<4><<<grid, kBlock, tbl, stream>>>(p);
+    } else if (n_limit <= 8) {
+      k_steps_uniform<8><<<grid, kBlock, tbl, stream>>>(p);
+    } else {
+      k_steps_uniform<0><<<grid, kBlock, tbl + state_bytes, stream>>>(p);
+    }
+  } else {
+    if (n_limit <= 4) {
+      k_steps_mixed<4><<<grid, kBlock, 0, stream>>>(p);
+    } else if (n_limit <= 8) {
+      k_steps_mixed<8><<<grid, kBlock, 0, stream>>>(p);
+    } else {
+      k_steps_mixed<0><<<grid, kBlock, state_bytes, stream>>>(p);
+    }
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_expand(const ExpandParams& p, int n_limit, cudaStream_t stream) {
+  if (p.N == 0) return cudaSuccess;
+  const unsigned grid = grid_for(p.N);
+  const size_t state_bytes = (size_t)p.n_max * 2 * kBlock * sizeof(int);
+  if (p.puzzle_id == nullptr) {
+    const size_t tbl = (size_t)p.uniform_u64 * 8;
+    if (n_limit <= 4) {
+      k_expand_uniform<4><<<grid, kBlock, tbl, stream>>>(p);
+    } else if (n_limit <= 8) {
+      k_expand_uniform<8><<<grid, kBlock, tbl, stream>>>(p);
+    } else {
+      k_expand_uniform<0><<<grid, kBlock, tbl + state_bytes, stream>>>(p);
+    }
+  } else {
+    if (n_limit <= 4) {
+      k_expand_mixed<4><<<grid, kBlock, 0, stream>>>(p);
+    } else if (n_limit <= 8) {
+      k_expand_mixed<8><<<grid, kBlock, 0, stream>>>(p);
+    } else {
+      k_expand_mixed<0><<<grid, kBlock, state_bytes, stream>>>(p);
+    }
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_reset(const ResetParams& p, cudaStream_t stream) {
+  if (p.N == 0) return cudaSuccess;
+  k_reset<<<grid_for(p.N), kBlock, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t configure_kernels(size_t max_dynamic_smem) {
+  // dynamic shared memory above 48 KB needs an explicit opt-in per kernel
+  cudaError_t err = cudaSuccess;
+#define PW_OPT_IN(k)                                                                             \
+  if (err == cudaSuccess)                                                                        \
+  err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_dynamic_smem)
+  PW_OPT_IN(k_steps_uniform<0>);
+  PW_OPT_IN(k_steps_uniform<4>);
+  PW_OPT_IN(k_steps_uniform<8>);
+  PW_OPT_IN(k_steps_mixed<0>);
+  PW_OPT_IN(k_expand_uniform<0>);
+  PW_OPT_IN(k_expand_uniform<4>);
+  PW_OPT_IN(k_expand_uniform<8>);
+  PW_OPT_IN(k_expand_mixed<0>);
+#undef PW_OPT_IN
+  return err;
+}
+
+}  // namespace pw

@@ -1,0 +1,299 @@
+"""``PushWorldVectorEnv``: N PushWorld environments stepped together on one GPU.
+
+The batched counterpart of the reference's single-environment wrappers: the same reward /
+terminated / truncated semantics as ``PushWorldEnv.step`` (python3/src/pushworld/gym_env.py:
+188-226) and the same padded float32 observation (utils/env_utils.py:44-91), for N
+environments per call.  As in the reference there is no implicit reset: stepping after
+``terminated`` keeps working (test_gym_env.py:89-102) unless ``autoreset=True``.
+
+All tensors live on the GPU; ``rollout_host`` is the host-buffer entry point (pinned host
+memory in, pinned host memory out, copies pipelined against the kernel on separate streams).
+"""
+
+from __future__ import annotations
+
+import os
+import random
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import data as _data
+from .engine import Engine, StepOutput
+from .utils.filesystem import iter_files_with_extension
+
+PUZZLE_EXTENSION = ".pwp"
+
+
+@dataclass
+class RolloutOutput:
+    reward: Optional[torch.Tensor]  # float32 [T, N]
+    terminated: Optional[torch.Tensor]  # uint8 [T, N]
+    dgoals: Optional[torch.Tensor] = None
+    truncated: Optional[torch.Tensor] = None
+    return_sum: Optional[torch.Tensor] = None  # float32 [N]
+    counters: Optional[torch.Tensor] = None  # int64 [4]
+
+
+def load_puzzle_texts(puzzle_path: str) -> List[str]:
+    """Reads every ``.pwp`` under ``puzzle_path`` in the reference's discovery order
+    (``os.walk``, utils/filesystem.py:21-61)."""
+    texts = []
+    for path in iter_files_with_extension(puzzle_path, PUZZLE_EXTENSION):
+        with open(path, "r") as f:
+            texts.append(f.read())
+    return texts
+
+
+class PushWorldVectorEnv:
+    """N environments over a set of puzzles.
+
+    Args:
+        puzzles: a path (file or directory, as ``PushWorldEnv``'s ``puzzle_path``) or a list of
+            ``.pwp`` texts.
+        num_envs: N.
+        puzzle_ids: per-environment puzzle index (sequence / tensor of length N), an int (all
+            environments share one puzzle -> the shared-memory table fast path), or None:
+            environment e gets puzzle ``e % num_puzzles`` and environments are then GROUPED by
+            puzzle (stable sort) so that a warp works on one puzzle; ``env_index`` maps slots
+            back to the round-robin numbering.
+        max_steps, border_width, pixels_per_cell, standard_padding: as ``PushWorldEnv``
+            (gym_env.py:57-64).
+        observation: None (no rendering), "float32" (the reference observation) or "uint8".
+    """
+
+    def __init__(
+        self,
+        puzzles: Union[str, Sequence[str]],
+        num_envs: int,
+        puzzle_ids: Union[None, int, Sequence[int], torch.Tensor] = None,
+        max_steps: Optional[int] = None,
+        border_width: int = 2,
+        pixels_per_cell: int = 20,
+        standard_padding: bool = False,
+        observation: Optional[str] = None,
+        device: Union[int, str, torch.device, None] = None,
+        autoreset: bool = False,
+    ) -> None:
+        texts = load_puzzle_texts(puzzles) if isinstance(puzzles, str) else list(puzzles)
+        if len(texts) == 0:
+            raise ValueError(f"No PushWorld puzzles found in: {puzzles}")
+        if border_width < 1:
+            raise ValueError("border_width must be >= 1")
+        if pixels_per_cell < 3:
+            raise ValueError("pixels_per_cell must be >= 3")
+        if observation not in (None, "float32", "uint8"):
+            raise ValueError("observation must be None, 'float32' or 'uint8'")
+        self.engine = Engine(texts, device=device)
+        self.device = self.engine.device
+        self.num_envs = int(num_envs)
+        self.max_steps = max_steps
+        self.border_width = border_width
+        self.pixels_per_cell = pixels_per_cell
+        self.observation = observation
+        self.autoreset = autoreset
+
+        max_h, max_w = self.engine.max_height, self.engine.max_width
+        if standard_padding:  # gym_env.py:86-105
+            std_h, std_w = _data.max_puzzle_dimensions()
+            if std_h < max_h or std_w < max_w:
+                raise ValueError(
+                    "`standard_padding` is True, but the benchmark's maximum puzzle size is "
+                    "smaller than the puzzle(s) in the given `puzzle_path`."
+                )
+            max_h, max_w = std_h, std_w
+        self.pad_cells = (max_h, max_w)
+
+        n = self.num_envs
+        if isinstance(puzzle_ids, int):
+            self._uniform: Optional[int] = puzzle_ids
+            self.puzzle_id = None
+            self.env_index = torch.arange(n, device=self.device)
+        else:
+            self._uniform = None
+            if puzzle_ids is None:
+                ids = torch.arange(n, dtype=torch.int64) % self.engine.num_puzzles
+                order = torch.argsort(ids, stable=True)
+                self.env_index = order.to(self.device)
+                ids = ids[order]
+            else:
+                ids = torch.as_tensor(puzzle_ids, dtype=torch.int64).cpu()
+                if ids.numel() != n:
+                    raise ValueError("puzzle_ids must have num_envs entries")
+                self.env_index = torch.arange(n, device=self.device)
+            if n and (ids.min() < 0 or ids.max() >= self.engine.num_puzzles):
+                raise ValueError("puzzle id out of range")
+            self.puzzle_id = ids.to(torch.int32).to(self.device)
+        self.xy = self.engine.new_state(n)
+        self.steps = torch.zeros(n, dtype=torch.int32, device=self.device)
+        self._is_reset = False
+        self._rng = random.Random(123)  # gym_env.py:109
+
+    # ------------------------------------------------------------------ helpers
+    @property
+    def _sel(self):
+        return self._uniform if self._uniform is not None else self.puzzle_id
+
+    @property
+    def observation_shape(self) -> Tuple[int, int, int]:
+        return (self.pad_cells[0] * self.pixels_per_cell, self.pad_cells[1] * self.pixels_per_cell, 3)
+
+    def _observe(self, out: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
+        if self.observation is None:
+            return None
+        return self.engine.render(self.xy, self._sel, dtype=self.observation,
+                                  pixels_per_cell=self.pixels_per_cell,
+                                  border_width=self.border_width, pad_cells=self.pad_cells, out=out)
+
+    def _require_reset(self) -> None:
+        if not self._is_reset:
+            raise RuntimeError("reset() must be called before step() can be called.")
+
+    def states(self) -> List[Tuple[Tuple[int, int], ...]]:
+        """Current states as python tuples (host copy; for inspection and tests)."""
+        host = self.xy.cpu().numpy()
+        if self._uniform is not None:
+            counts = [self.engine.parsed[self._uniform].num_objects] * self.num_envs
+        else:
+            per_puzzle = [p.num_objects for p in self.engine.parsed]
+            counts = [per_puzzle[i] for i in self.puzzle_id.cpu().tolist()]
+        return [
+            tuple((int(host[0, j, e]), int(host[1, j, e])) for j in range(counts[e]))
+            for e in range(self.num_envs)
+        ]
+
+    # ------------------------------------------------------------------ gym-like surface
+    def reset(self, seed: Optional[int] = None, mask: Optional[torch.Tensor] = None):
+        """All (or the masked) environments go back to their puzzle's initial state."""
+        if seed is not None:
+            self._rng = random.Random(seed)
+        self.engine.reset(self.xy, self._sel, steps=self.steps, mask=mask)
+        self._is_reset = True
+        return self._observe()
+
+    def step(self, actions: torch.Tensor, check_actions: bool = True):
+        """-> (observation or None, reward f32 [N], terminated u8 [N], truncated u8 [N], info)"""
+        self._require_reset()
+        actions = self._as_actions(actions, (self.num_envs,))
+        if self.observation is None:
+            out = self.engine.step(self.xy, self._sel, actions, steps=self.steps,
+                                   max_steps=self.max_steps)
+            obs = None
+        else:
+            obs, out = self.engine.step_render(
+                self.xy, self._sel, actions, dtype=self.observation,
+                pixels_per_cell=self.pixels_per_cell, border_width=self.border_width,
+                pad_cells=self.pad_cells, steps=self.steps, max_steps=self.max_steps)
+        if check_actions and self.engine.poll_invalid_actions():
+            raise ValueError("The provided action is not in the action space.")  # gym_env.py:195
+        return obs, out.reward, out.terminated, out.truncated, {"dgoals": out.dgoals}
+
+    def _as_actions(self, actions, shape) -> torch.Tensor:
+        if not isinstance(actions, torch.Tensor):
+            actions = torch.as_tensor(np.asarray(actions))
+        if actions.dtype != torch.uint8:
+            if actions.numel() and (actions.min() < 0 or actions.max() > 255):
+                raise ValueError("The provided action is not in the action space.")
+            actions = actions.to(torch.uint8)
+        actions = actions.to(self.device).contiguous()
+        if tuple(actions.shape) != tuple(shape):
+            raise ValueError(f"actions must have shape {tuple(shape)}")
+        return actions
+
+    def rollout(self, actions: torch.Tensor, want_reward: bool = True, want_terminated: bool = True,
+                want_dgoals: bool = False, want_truncated: bool = False,
+                out: Optional[RolloutOutput] = None) -> RolloutOutput:
+        """T fused steps in one launch; ``actions`` uint8 ``[T, N]`` on the device."""
+        self._require_reset()
+        if actions.dim() != 2:
+            raise ValueError("actions must have shape [T, N]")
+        actions = self._as_actions(actions, (actions.shape[0], self.num_envs))
+        t, n = actions.shape
+        dev = self.device
+        if out is None:
+            out = RolloutOutput(
+                reward=torch.empty((t, n), dtype=torch.float32, device=dev) if want_reward else None,
+                terminated=torch.empty((t, n), dtype=torch.uint8, device=dev) if want_terminated else None,
+                dgoals=torch.empty((t, n), dtype=torch.int8, device=dev) if want_dgoals else None,
+                truncated=torch.empty((t, n), dtype=torch.uint8, device=dev) if want_truncated else None,
+                return_sum=torch.zeros(n, dtype=torch.float32, device=dev),
+                counters=torch.zeros(4, dtype=torch.int64, device=dev),
+            )
+        self.engine.rollout(self.xy, self._sel, actions, reward=out.reward, terminated=out.terminated,
+                            dgoals=out.dgoals, truncated=out.truncated, steps=self.steps,
+                            max_steps=self.max_steps, return_sum=out.return_sum,
+                            counters=out.counters, autoreset=self.autoreset)
+        return out
+
+    # ------------------------------------------------------------------ host-buffer entry point
+    def rollout_host(self, actions: torch.Tensor, reward: torch.Tensor, terminated: torch.Tensor,
+                     chunk_steps: int = 64) -> None:
+        """``actions`` (uint8 [T, N]), ``reward`` (float32 [T, N]) and ``terminated`` (uint8
+        [T, N]) are PINNED HOST tensors.  The T steps are cut into chunks; chunk k's
+        host->device copy, chunk k-1's kernel and chunk k-2's device->host copies run
+        concurrently on three streams (both PCIe directions stay busy).  Blocks until the
+        outputs are in host memory."""
+        self._require_reset()
+        t, n = actions.shape
+        assert n == self.num_envs and reward.shape == (t, n) and terminated.shape == (t, n)
+        assert actions.is_pinned() and reward.is_pinned() and terminated.is_pinned()
+        pipe = self._host_pipe(chunk_steps)
+        pipe.run(self, actions, reward, terminated)
+
+    def _host_pipe(self, chunk_steps: int):
+        pipe = getattr(self, "_pipe", None)
+        if pipe is None or pipe.chunk != chunk_steps:
+            pipe = _HostPipe(self.device, self.num_envs, chunk_steps)
+            self._pipe = pipe
+        return pipe
+
+
+class _HostPipe:
+    """Three-stream software pipeline for ``rollout_host`` with double-buffered device staging."""
+
+    DEPTH = 3
+
+    def __init__(self, device, n: int, chunk: int):
+        self.chunk = chunk
+        self.s_in = torch.cuda.Stream(device)
+        self.s_run = torch.cuda.Stream(device)
+        self.s_out = torch.cuda.Stream(device)
+        mk = lambda dt: [torch.empty((chunk, n), dtype=dt, device=device) for _ in range(self.DEPTH)]
+        self.d_act, self.d_rew, self.d_term = mk(torch.uint8), mk(torch.float32), mk(torch.uint8)
+        self.ev_in = [torch.cuda.Event() for _ in range(self.DEPTH)]
+        self.ev_run = [torch.cuda.Event() for _ in range(self.DEPTH)]
+        self.ev_out = [torch.cuda.Event() for _ in range(self.DEPTH)]
+
+    def run(self, env: "PushWorldVectorEnv", actions, reward, terminated) -> None:
+        t = actions.shape[0]
+        cur = torch.cuda.current_stream(env.device)
+        for s in (self.s_in, self.s_run, self.s_out):
+            s.wait_stream(cur)
+        n_chunks = (t + self.chunk - 1) // self.chunk
+        for k in range(n_chunks):
+            b = k % self.DEPTH
+            lo, hi = k * self.chunk, min(t, (k + 1) * self.chunk)
+            m = hi - lo
+            with torch.cuda.stream(self.s_in):
+                if k >= self.DEPTH:
+                    self.s_in.wait_event(self.ev_run[b])  # kernel k-DEPTH done with d_act[b]
+                self.d_act[b][:m].copy_(actions[lo:hi], non_blocking=True)
+                self.ev_in[b].record(self.s_in)
+            with torch.cuda.stream(self.s_run):
+                self.s_run.wait_event(self.ev_in[b])
+                if k >= self.DEPTH:
+                    self.s_run.wait_event(self.ev_out[b])  # outputs of chunk k-DEPTH copied out
+                env.engine.rollout(env.xy, env._sel, self.d_act[b][:m], reward=self.d_rew[b][:m],
+                                   terminated=self.d_term[b][:m], steps=env.steps,
+                                   max_steps=env.max_steps, autoreset=env.autoreset)
+                self.ev_run[b].record(self.s_run)
+            with torch.cuda.stream(self.s_out):
+                self.s_out.wait_event(self.ev_run[b])
+                reward[lo:hi].copy_(self.d_rew[b][:m], non_blocking=True)
+                terminated[lo:hi].copy_(self.d_term[b][:m], non_blocking=True)
+                self.ev_out[b].record(self.s_out)
+        cur.wait_stream(self.s_out)
+        cur.wait_stream(self.s_run)
+        cur.synchronize()

@@ -1,0 +1,109 @@
+// CPU-side check harness (TEST INFRASTRUCTURE): compiles the very transition rule the CUDA
+// kernels use (pushworld_b200/csrc/pw_core.cuh is host/device code) with g++ so that the
+// bit logic can be checked against the oracle and the golden vectors without a GPU.
+// Never linked into, or reachable from, the product library.
+#include <stdint.h>
+#include <string.h>
+
+#include "pw_core.cuh"
+#include "pw_render_core.cuh"
+
+namespace {
+
+struct HostEnv {
+  static constexpr int kStaticN = 0;
+  static constexpr int kUnroll = 1;
+  const uint64_t* base;
+  int n_, g_, w_, h_, wall_off_, awall_off_, desc_word_;
+  int* px;
+  int* py;
+  uint32_t word(int i) const { return reinterpret_cast<const uint32_t*>(base)[i]; }
+  void init(const uint64_t* b, int* x, int* y) {
+    base = b;
+    px = x;
+    py = y;
+    w_ = word(pw::kHdrDims) & 0xffff;
+    h_ = word(pw::kHdrDims) >> 16;
+    n_ = word(pw::kHdrCounts) & 0xffff;
+    g_ = word(pw::kHdrCounts) >> 16;
+    wall_off_ = word(pw::kHdrWallOff);
+    awall_off_ = word(pw::kHdrAwallOff);
+    desc_word_ = word(pw::kHdrObjOff) * 2;
+  }
+  int n() const { return n_; }
+  int g() const { return g_; }
+  int width() const { return w_; }
+  int height() const { return h_; }
+  int wall_off() const { return wall_off_; }
+  int awall_off() const { return awall_off_; }
+  uint64_t row(int off) const { return base[off]; }
+  uint32_t desc(int j) const { return word(desc_word_ + 4 * j); }
+  uint32_t desc_dyn(int j) const { return desc(j); }
+  int x(int j) const { return px[j]; }
+  int y(int j) const { return py[j]; }
+  int x_dyn(int j) const { return px[j]; }
+  int y_dyn(int j) const { return py[j]; }
+  int goal_x(int k) const { return pw::lo16(word(desc_word_ + 4 * (k + 1) + 2)); }
+  int goal_y(int k) const { return pw::hi16(word(desc_word_ + 4 * (k + 1) + 2)); }
+  void translate(uint32_t mask, int dx, int dy) {
+    for (int j = 0; j < n_; ++j)
+      if ((mask >> j) & 1u) {
+        px[j] += dx;
+        py[j] += dy;
+      }
+  }
+};
+
+}  // namespace
+
+struct HostTable {
+  const uint64_t* base;
+  uint64_t row(int off) const { return base[off]; }
+  uint32_t word(int i) const { return reinterpret_cast<const uint32_t*>(base)[i]; }
+};
+struct HostPos {
+  const int* px;
+  const int* py;
+  int x(int j) const { return px[j]; }
+  int y(int j) const { return py[j]; }
+};
+
+extern "C" {
+
+// Expands pw::cell_code() into a uint8 image [H*ppc][W*ppc][3] (the CUDA kernel does the same
+// expansion with shared-memory row patterns; this loop is deliberately the naive one).
+void hc_render_u8(const uint64_t* blob, const int* x, const int* y, int ppc, int bw,
+                  const uint8_t* palette /*[16][3]*/, uint8_t* out) {
+  HostTable t{blob};
+  HostPos pos{x, y};
+  const int W = t.word(pw::kHdrDims) & 0xffff, H = t.word(pw::kHdrDims) >> 16;
+  for (int cy = 0; cy < H; ++cy)
+    for (int cx = 0; cx < W; ++cx) {
+      const uint64_t code = pw::cell_code(t, pos, cx, cy);
+      for (int oy = 0; oy < ppc; ++oy)
+        for (int ox = 0; ox < ppc; ++ox) {
+          const int k = pw::region_of(oy, ppc, bw) * 3 + pw::region_of(ox, ppc, bw);
+          const int pal = (int)((code >> (4 * k)) & 15);
+          uint8_t* px = out + ((size_t)(cy * ppc + oy) * (size_t)(W * ppc) + (size_t)(cx * ppc + ox)) * 3;
+          px[0] = palette[pal * 3 + 0];
+          px[1] = palette[pal * 3 + 1];
+          px[2] = palette[pal * 3 + 2];
+        }
+    }
+}
+
+// Applies `n_actions` actions in sequence to one environment, recording after every action the
+// state (xs/ys: [n_actions][n]), the moved mask and the achieved-goal count.
+int hc_walk(const uint64_t* blob, int* x, int* y, const uint8_t* actions, int n_actions,
+            int* xs, int* ys, uint32_t* moved, int* achieved) {
+  HostEnv env;
+  env.init(blob, x, y);
+  for (int t = 0; t < n_actions; ++t) {
+    moved[t] = pw::step(env, actions[t]);
+    achieved[t] = pw::achieved_goals(env);
+    memcpy(xs + (size_t)t * env.n(), x, sizeof(int) * env.n());
+    memcpy(ys + (size_t)t * env.n(), y, sizeof(int) * env.n());
+  }
+  return env.n();
+}
+}

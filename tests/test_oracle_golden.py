@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 import pushworld_oracle as po
-from conftest import GOLDEN
+from tests.conftest import GOLDEN
 
 
 def _states(arr):
@@ -97,7 +97,7 @@ def test_env_logic_matches_reference_gym(golden):
 
 def test_reference_known_answers():
     """python3/test/test_puzzle.py:69-98 restated against the oracle."""
-    import conftest
+    from tests import conftest
 
     g = conftest.Golden()
     p = po.OraclePuzzle(g.text("python3/pushing"))
@@ -118,3 +118,38 @@ def test_reference_known_answers():
         po.OraclePuzzle(". m0\n. .\n")
     with pytest.raises(AssertionError):
         po.OraclePuzzle("a g1\n. m0\n")
+
+
+def test_c_oracle_matches_reference(golden):
+    """oracle/pw_oracle.c (table-driven, the reference's own algorithm) on every golden
+    transition, plus the batched rollout entry point used as the CPU baseline."""
+    import c_oracle
+
+    checked = 0
+    for key in golden.keys():
+        cp = c_oracle.COraclePuzzle(golden.text(key))
+        for tag in ("sol", "walk"):
+            if not golden.has(key, f"{tag}_actions"):
+                continue
+            actions = golden.arr(key, f"{tag}_actions")
+            states = _states(golden.arr(key, f"{tag}_states"))
+            achieved = golden.arr(key, f"{tag}_achieved")
+            for t, a in enumerate(actions):
+                nxt, moved = cp.step(states[t], int(a))
+                assert nxt == states[t + 1], (key, tag, t)
+                changed = sum(1 << k for k in range(cp.n) if states[t][k] != states[t + 1][k])
+                assert moved == changed
+                checked += 1
+            assert cp.achieved(states[-1]) == achieved[-1]
+        if golden.has(key, "walk_actions"):
+            acts = np.ascontiguousarray(np.repeat(golden.arr(key, "walk_actions")[:, None], 3, axis=1))
+            init = golden.arr(key, "walk_states").astype(np.int32)[0]
+            x = np.ascontiguousarray(np.repeat(init[:, 0:1], 3, axis=1))
+            y = np.ascontiguousarray(np.repeat(init[:, 1:2], 3, axis=1))
+            reward = np.zeros(acts.shape, np.float32)
+            term = np.zeros(acts.shape, np.uint8)
+            cp.rollout(x, y, acts, reward, term, threads=2)
+            final = golden.arr(key, "walk_states").astype(np.int32)[-1]
+            assert (x == final[:, 0:1]).all() and (y == final[:, 1:2]).all(), key
+            assert np.array_equal(term[:, 0].astype(bool), golden.arr(key, "walk_isgoal")[1:])
+    assert checked > 85000
