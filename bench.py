@@ -227,7 +227,6 @@ def run_ours(args) -> None:
     out = RolloutOutput(
         reward=torch.empty((T_STEPS, N_ENVS), dtype=torch.float32, device=dev),
         terminated=torch.empty((T_STEPS, N_ENVS), dtype=torch.uint8, device=dev),
-        return_sum=torch.zeros(N_ENVS, dtype=torch.float32, device=dev),
         counters=torch.zeros(4, dtype=torch.int64, device=dev),
     )
 

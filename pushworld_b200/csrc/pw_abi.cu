@@ -76,6 +76,15 @@ int check_common(const PwEngine* e, int64_t n, const int32_t* puzzle_id, int puz
   return PW_OK;
 }
 
+// An empty batch is a successful no-op whatever the pointers are (empty tensors have NULL data).
+#define PW_RETURN_IF_EMPTY(n) \
+  if ((n) == 0) return PW_OK
+
+// bitboard kernel: the whole grid fits one uint64 and the puzzle starts in a regular state
+int board_eligible(const PuzzleInfo& info) {
+  return (info.width * info.height <= 64 && (info.flags & PW_TABLE_FLAG_REGULAR)) ? 1 : 0;
+}
+
 int n_limit_of(const PwEngine* e, const int32_t* puzzle_id, int puzzle_uniform) {
   return puzzle_id ? e->n_max : e->puzzles[(size_t)puzzle_uniform].n;
 }
@@ -241,6 +250,7 @@ int pw_reset(PwEngine* e, int64_t n_envs, const int32_t* puzzle_id, int puzzle_u
   clear_error();
   const int rc = check_common(e, n_envs, puzzle_id, puzzle_uniform, stride, n_envs);
   if (rc != PW_OK) return rc;
+  PW_RETURN_IF_EMPTY(n_envs);
   if (x == nullptr || y == nullptr) return set_error(PW_E_INVALID, "x / y is NULL");
   DeviceGuard guard(e->device);
   ResetParams p{};
@@ -267,6 +277,7 @@ int pw_rollout(PwEngine* e, int64_t n_envs, int32_t n_steps, const int32_t* puzz
   clear_error();
   const int rc = check_common(e, n_envs, puzzle_id, puzzle_uniform, stride, n_envs);
   if (rc != PW_OK) return rc;
+  PW_RETURN_IF_EMPTY(n_envs);
   if (n_steps < 0) return set_error(PW_E_INVALID, "negative step count");
   if (x == nullptr || y == nullptr || actions == nullptr)
     return set_error(PW_E_INVALID, "x / y / actions is NULL");
@@ -281,6 +292,7 @@ int pw_rollout(PwEngine* e, int64_t n_envs, int32_t n_steps, const int32_t* puzz
   p.puzzle_uniform = puzzle_id ? 0 : puzzle_uniform;
   p.uniform_u64 = puzzle_id ? 0 : e->puzzles[(size_t)puzzle_uniform].size_u64;
   p.n_max = e->n_max;
+  p.board_ok = puzzle_id ? 0 : board_eligible(e->puzzles[(size_t)puzzle_uniform]);
   p.x = x;
   p.y = y;
   p.stride = stride;
@@ -308,6 +320,7 @@ int pw_step(PwEngine* e, int64_t n_envs, const int32_t* puzzle_id, int puzzle_un
   clear_error();
   const int rc = check_common(e, n_envs, puzzle_id, puzzle_uniform, stride, n_envs);
   if (rc != PW_OK) return rc;
+  PW_RETURN_IF_EMPTY(n_envs);
   if (x == nullptr || y == nullptr || action == nullptr)
     return set_error(PW_E_INVALID, "x / y / action is NULL");
   DeviceGuard guard(e->device);
@@ -320,6 +333,7 @@ int pw_step(PwEngine* e, int64_t n_envs, const int32_t* puzzle_id, int puzzle_un
   p.puzzle_uniform = puzzle_id ? 0 : puzzle_uniform;
   p.uniform_u64 = puzzle_id ? 0 : e->puzzles[(size_t)puzzle_uniform].size_u64;
   p.n_max = e->n_max;
+  p.board_ok = puzzle_id ? 0 : board_eligible(e->puzzles[(size_t)puzzle_uniform]);
   p.x = x;
   p.y = y;
   p.stride = stride;
@@ -346,6 +360,7 @@ int pw_expand(PwEngine* e, int64_t n_states, const int32_t* puzzle_id, int puzzl
   clear_error();
   int rc = check_common(e, n_states, puzzle_id, puzzle_uniform, stride_in, n_states);
   if (rc != PW_OK) return rc;
+  PW_RETURN_IF_EMPTY(n_states);
   if (stride_out < 4 * n_states) return set_error(PW_E_INVALID, "stride_out smaller than 4*N");
   if (x_in == nullptr || y_in == nullptr || x_out == nullptr || y_out == nullptr)
     return set_error(PW_E_INVALID, "state pointer is NULL");
@@ -418,6 +433,7 @@ int pw_render(PwEngine* e, int64_t n_envs, const int32_t* puzzle_id, int puzzle_
   clear_error();
   const int rc = check_common(e, n_envs, puzzle_id, puzzle_uniform, stride, n_envs);
   if (rc != PW_OK) return rc;
+  PW_RETURN_IF_EMPTY(n_envs);
   return render_common(e, n_envs, puzzle_id, puzzle_uniform, x, y, stride, out, dtype,
                        pixels_per_cell, border_width, pad_h_cells, pad_w_cells, nullptr, stream,
                        "pw_render");
@@ -431,6 +447,7 @@ int pw_step_render(PwEngine* e, int64_t n_envs, const int32_t* puzzle_id, int pu
   clear_error();
   const int rc = check_common(e, n_envs, puzzle_id, puzzle_uniform, stride, n_envs);
   if (rc != PW_OK) return rc;
+  PW_RETURN_IF_EMPTY(n_envs);
   if (action == nullptr) return set_error(PW_E_INVALID, "action is NULL");
   StepParams p{};
   p.blob = e->d_blob;
@@ -441,6 +458,7 @@ int pw_step_render(PwEngine* e, int64_t n_envs, const int32_t* puzzle_id, int pu
   p.puzzle_uniform = puzzle_id ? 0 : puzzle_uniform;
   p.uniform_u64 = puzzle_id ? 0 : e->puzzles[(size_t)puzzle_uniform].size_u64;
   p.n_max = e->n_max;
+  p.board_ok = puzzle_id ? 0 : board_eligible(e->puzzles[(size_t)puzzle_uniform]);
   p.x = x;
   p.y = y;
   p.stride = stride;

@@ -198,4 +198,51 @@ struct SmemEnv : EnvBase<Table> {
   }
 };
 
+// Positions in (per-thread) local memory: the slow-path policy for the rare environments a
+// specialised kernel cannot take (e.g. an irregular state handed to the bitboard kernel).
+template <class Table>
+struct LocalEnv : EnvBase<Table> {
+  static constexpr int kStaticN = 0;
+  static constexpr int kUnroll = 1;
+  int px[kMaxObjects], py[kMaxObjects];
+
+  __device__ __forceinline__ void init(Table table) { this->init_header(table); }
+  __device__ __forceinline__ void load(const int32_t* x, const int32_t* y, int64_t stride,
+                                       int64_t e) {
+    for (int j = 0; j < this->n_; ++j) {
+      px[j] = x[j * stride + e];
+      py[j] = y[j * stride + e];
+    }
+  }
+  __device__ __forceinline__ void load_initial() {
+    for (int j = 0; j < this->n_; ++j) {
+      const uint32_t v = this->table_desc(j, 1);
+      px[j] = lo16(v);
+      py[j] = hi16(v);
+    }
+  }
+  __device__ __forceinline__ void store(int32_t* x, int32_t* y, int64_t stride, int64_t e) const {
+    for (int j = 0; j < this->n_; ++j) {
+      x[j * stride + e] = px[j];
+      y[j * stride + e] = py[j];
+    }
+  }
+  __device__ __forceinline__ uint32_t desc(int j) const { return this->table_desc(j, 0); }
+  __device__ __forceinline__ uint32_t desc_dyn(int j) const { return this->table_desc(j, 0); }
+  __device__ __forceinline__ int x(int j) const { return px[j]; }
+  __device__ __forceinline__ int y(int j) const { return py[j]; }
+  __device__ __forceinline__ int x_dyn(int j) const { return px[j]; }
+  __device__ __forceinline__ int y_dyn(int j) const { return py[j]; }
+  __device__ __forceinline__ int goal_x(int k) const { return lo16(this->table_desc(k + 1, 2)); }
+  __device__ __forceinline__ int goal_y(int k) const { return hi16(this->table_desc(k + 1, 2)); }
+  __device__ __forceinline__ void translate(uint32_t mask, int dx, int dy) {
+    while (mask) {
+      const int j = __ffs((int)mask) - 1;
+      mask &= mask - 1;
+      px[j] += dx;
+      py[j] += dy;
+    }
+  }
+};
+
 }  // namespace pw

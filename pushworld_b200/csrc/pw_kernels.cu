@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "pw_board.cuh"
 #include "pw_env.cuh"
 #include "pw_internal.h"
 #include "pw_steps.cuh"
@@ -17,6 +18,7 @@ cudaError_t upload_reward_lut(const float* host_lut) {
 
 namespace {
 
+#define COMMA ,
 constexpr int kBlock = 128;
 
 // Copies one puzzle blob into shared memory (all threads of the block take part).
@@ -34,11 +36,8 @@ __device__ __forceinline__ uint32_t warp_sum(uint32_t v) {
 // ------------------------------------------------------------------------------------------
 // T fused steps of one environment per thread (pw_steps.cuh) + block-level counter flush.
 // ------------------------------------------------------------------------------------------
-template <class Env>
-__device__ __forceinline__ void run_steps(Env& env, const StepParams& p, int64_t e, bool active,
-                                          uint32_t* s_counters) {
-  StepCounts c;
-  if (active) run_steps_thread(env, p, e, c);
+__device__ __forceinline__ void flush_counts(const StepCounts& c, const StepParams& p,
+                                             uint32_t* s_counters) {
   if (p.counters || p.status) {
     const uint32_t c_term = warp_sum(c.terminated), c_moved = warp_sum(c.moved);
     const uint32_t c_dg = warp_sum(c.dgoals), c_invalid = warp_sum(c.invalid);
@@ -64,10 +63,19 @@ __device__ __forceinline__ void run_steps(Env& env, const StepParams& p, int64_t
   }
 }
 
+template <bool kLean, class Env>
+__device__ __forceinline__ void run_steps(Env& env, const StepParams& p, int64_t e, bool active,
+                                          uint32_t* s_counters) {
+  StepCounts c;
+  if (active) run_steps_thread<kLean>(env, p, e, c);
+  flush_counts(c, p, s_counters);
+}
+
 // All environments of the launch share puzzle `p.puzzle_uniform`: its table is staged in
 // shared memory once per block.
-template <int NMAX>
-__global__ void __launch_bounds__(kBlock) k_steps_uniform(const StepParams p) {
+template <int NMAX, bool kLean>
+__global__ void __launch_bounds__(kBlock)
+    k_steps_uniform(const __grid_constant__ StepParams p) {
   extern __shared__ uint64_t smem[];
   __shared__ uint32_t s_counters[4];
   if (threadIdx.x < 4) s_counters[threadIdx.x] = 0;
@@ -78,19 +86,114 @@ __global__ void __launch_bounds__(kBlock) k_steps_uniform(const StepParams p) {
   if constexpr (NMAX > 0) {
     RegEnv<NMAX, SharedTable> env;
     env.init(SharedTable{smem});
-    run_steps(env, p, e, active, s_counters);
+    run_steps<kLean>(env, p, e, active, s_counters);
   } else {
     SmemEnv<SharedTable> env;
     int* st = reinterpret_cast<int*>(smem + p.uniform_u64);
     env.init(SharedTable{smem}, st + threadIdx.x, st + p.n_max * kBlock + threadIdx.x, kBlock);
-    run_steps(env, p, e, active, s_counters);
+    run_steps<kLean>(env, p, e, active, s_counters);
   }
+}
+
+// ------------------------------------------------------------------------------------------
+// Bitboard kernel: single puzzle with width*height <= 64 and n <= NMAX (pw_board.cuh).  The whole
+// per-step state of an environment is NMAX uint64 registers and a step is branch-light shift /
+// and / or work.  Environments whose loaded state is not regular take the general rule through
+// a non-inlined slow path (positions in local memory), so results are exact for any input.
+// ------------------------------------------------------------------------------------------
+// per-block static boards, computed once by a few threads
+struct BoardStatic {
+  uint64_t wall, awall;
+  uint64_t goal[8];
+  uint64_t init[8];
+  int W, n, g;
+};
+
+template <int NMAX>
+struct BoardSim {
+  static constexpr bool kCheapAchieved = true;
+  Board<NMAX>& s;
+  const BoardStatic& st;
+  __device__ __forceinline__ void store(const StepParams& p, int64_t e) {
+#pragma unroll
+    for (int k = 0; k < NMAX; ++k)
+      if (k < s.n) {
+        int x, y;
+        board_position(s.b[k], s.W, &x, &y);
+        p.x[k * p.stride + e] = x;
+        p.y[k * p.stride + e] = y;
+      }
+  }
+  __device__ __forceinline__ void load_initial() {
+#pragma unroll
+    for (int k = 0; k < NMAX; ++k) s.b[k] = st.init[k];
+  }
+  __device__ __forceinline__ uint32_t do_step(int a) { return board_step(s, a); }
+  __device__ __forceinline__ int achieved() const { return board_achieved(s); }
+  __device__ __forceinline__ int goals() const { return s.g; }
+};
+
+__device__ __noinline__ void general_slow_path(const uint64_t* table, const StepParams& p, int64_t e,
+                                               StepCounts& c) {
+  LocalEnv<SharedTable> env;
+  env.init(SharedTable{table});
+  run_steps_thread<false>(env, p, e, c);
+}
+
+template <int NMAX, int MIN_BLOCKS, bool kLean>
+__global__ void __launch_bounds__(kBlock, MIN_BLOCKS)
+    k_steps_board(const __grid_constant__ StepParams p) {
+  extern __shared__ uint64_t smem[];
+  __shared__ uint32_t s_counters[4];
+  __shared__ BoardStatic st;
+  if (threadIdx.x < 4) s_counters[threadIdx.x] = 0;
+  stage_table(smem, p.blob + p.puzzle_off[p.puzzle_uniform], p.uniform_u64);
+  const SharedTable tbl{smem};
+  if (threadIdx.x == 0) {
+    Board<NMAX> tmp;
+    board_init(tmp, tbl);
+    const int desc_word = (int)tbl.word(kHdrObjOff) * 2;
+    board_load(tmp, tbl, [&](int k) { return lo16(tbl.word(desc_word + 4 * k + 1)); },
+               [&](int k) { return hi16(tbl.word(desc_word + 4 * k + 1)); });
+    st.wall = tmp.wall;
+    st.awall = tmp.awall;
+    st.W = tmp.W;
+    st.n = tmp.n;
+    st.g = tmp.g;
+    for (int k = 0; k < NMAX; ++k) {
+      st.goal[k] = tmp.goal[k];
+      st.init[k] = tmp.b[k];
+    }
+  }
+  __syncthreads();
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  StepCounts c;
+  if (e < p.N) {
+    Board<NMAX> s;
+    s.wall = st.wall;
+    s.awall = st.awall;
+    s.W = st.W;
+    s.n = st.n;
+    s.g = st.g;
+#pragma unroll
+    for (int k = 0; k < NMAX; ++k) s.goal[k] = st.goal[k];
+    const bool regular = board_load(s, tbl, [&](int k) { return p.x[k * p.stride + e]; },
+                                    [&](int k) { return p.y[k * p.stride + e]; });
+    if (regular) {
+      BoardSim<NMAX> sim{s, st};
+      run_steps_sim<kLean>(sim, p, e, c);
+    } else {
+      general_slow_path(smem, p, e, c);
+    }
+  }
+  flush_counts(c, p, s_counters);
 }
 
 // Per-environment puzzle ids: tables are read from global memory (L1/L2 resident, the whole
 // benchmark set is < 1 MB).
-template <int NMAX>
-__global__ void __launch_bounds__(kBlock) k_steps_mixed(const StepParams p) {
+template <int NMAX, bool kLean>
+__global__ void __launch_bounds__(kBlock)
+    k_steps_mixed(const __grid_constant__ StepParams p) {
   extern __shared__ uint64_t smem[];
   __shared__ uint32_t s_counters[4];
   if (threadIdx.x < 4) s_counters[threadIdx.x] = 0;
@@ -102,12 +205,12 @@ __global__ void __launch_bounds__(kBlock) k_steps_mixed(const StepParams p) {
   if constexpr (NMAX > 0) {
     RegEnv<NMAX, GlobalTable> env;
     env.init(table);
-    run_steps(env, p, e, active, s_counters);
+    run_steps<kLean>(env, p, e, active, s_counters);
   } else {
     SmemEnv<GlobalTable> env;
     int* st = reinterpret_cast<int*>(smem);
     env.init(table, st + threadIdx.x, st + p.n_max * kBlock + threadIdx.x, kBlock);
-    run_steps(env, p, e, active, s_counters);
+    run_steps<kLean>(env, p, e, active, s_counters);
   }
 }
 
@@ -202,24 +305,44 @@ cudaError_t launch_steps(const StepParams& p, int n_limit, cudaStream_t stream) 
   if (p.N == 0 || p.T == 0) return cudaSuccess;
   const unsigned grid = grid_for(p.N);
   const size_t state_bytes = (size_t)p.n_max * 2 * kBlock * sizeof(int);
+  const bool lean = is_lean(p);
+#define PW_GO(kernel, smem_bytes)                                         \
+  do {                                                                    \
+    if (lean)                                                             \
+      kernel, true><<<grid, kBlock, smem_bytes, stream>>>(p);             \
+    else                                                                  \
+      kernel, false><<<grid, kBlock, smem_bytes, stream>>>(p);            \
+  } while (0)
   if (p.puzzle_id == nullptr) {
     const size_t tbl = (size_t)p.uniform_u64 * 8;
-    if (n_limit <= 4) {
-      k_steps_uniform<4><<<grid, kBlock, tbl, stream>>>(p);
+    if (p.board_ok && n_limit <= 8) {  // exact-n instantiations of the bitboard kernel
+      switch (n_limit) {
+        case 1:
+        case 2: PW_GO(k_steps_board<2 COMMA 8, tbl); break;
+        case 3: PW_GO(k_steps_board<3 COMMA 8, tbl); break;
+        case 4: PW_GO(k_steps_board<4 COMMA 8, tbl); break;
+        case 5: PW_GO(k_steps_board<5 COMMA 8, tbl); break;
+        case 6: PW_GO(k_steps_board<6 COMMA 8, tbl); break;
+        case 7: PW_GO(k_steps_board<7 COMMA 6, tbl); break;
+        default: PW_GO(k_steps_board<8 COMMA 6, tbl); break;
+      }
+    } else if (n_limit <= 4) {
+      PW_GO(k_steps_uniform<4, tbl);
     } else if (n_limit <= 8) {
-      k_steps_uniform<8><<<grid, kBlock, tbl, stream>>>(p);
+      PW_GO(k_steps_uniform<8, tbl);
     } else {
-      k_steps_uniform<0><<<grid, kBlock, tbl + state_bytes, stream>>>(p);
+      PW_GO(k_steps_uniform<0, tbl + state_bytes);
     }
   } else {
     if (n_limit <= 4) {
-      k_steps_mixed<4><<<grid, kBlock, 0, stream>>>(p);
+      PW_GO(k_steps_mixed<4, 0);
     } else if (n_limit <= 8) {
-      k_steps_mixed<8><<<grid, kBlock, 0, stream>>>(p);
+      PW_GO(k_steps_mixed<8, 0);
     } else {
-      k_steps_mixed<0><<<grid, kBlock, state_bytes, stream>>>(p);
+      PW_GO(k_steps_mixed<0, state_bytes);
     }
   }
+#undef PW_GO
   return cudaGetLastError();
 }
 
@@ -260,10 +383,10 @@ cudaError_t configure_kernels(size_t max_dynamic_smem) {
 #define PW_OPT_IN(k)                                                                             \
   if (err == cudaSuccess)                                                                        \
   err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_dynamic_smem)
-  PW_OPT_IN(k_steps_uniform<0>);
-  PW_OPT_IN(k_steps_uniform<4>);
-  PW_OPT_IN(k_steps_uniform<8>);
-  PW_OPT_IN(k_steps_mixed<0>);
+  PW_OPT_IN((k_steps_uniform<0, true>));
+  PW_OPT_IN((k_steps_uniform<0, false>));
+  PW_OPT_IN((k_steps_mixed<0, true>));
+  PW_OPT_IN((k_steps_mixed<0, false>));
   PW_OPT_IN(k_expand_uniform<0>);
   PW_OPT_IN(k_expand_uniform<4>);
   PW_OPT_IN(k_expand_uniform<8>);

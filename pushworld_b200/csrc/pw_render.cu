@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(kRenderBlock) k_render(const RenderParams p, c
       SmemEnv<SharedTable> env;
       env.init(tbl, s_x, s_y, 1);
       StepCounts counts;
-      run_steps_thread(env, sp, e, counts);
+      run_steps_thread<false>(env, sp, e, counts);
       if (counts.invalid && sp.status) atomicAdd(&sp.status[0], (unsigned long long)counts.invalid);
     }
   } else {

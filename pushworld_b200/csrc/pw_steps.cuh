@@ -18,47 +18,101 @@ struct StepCounts {
   uint32_t terminated = 0, moved = 0, dgoals = 0, invalid = 0;
 };
 
+// Adaptor: an Env policy (pw_env.cuh) driven by the general rule of pw_core.cuh.
 template <class Env>
-__device__ __forceinline__ void run_steps_thread(Env& env, const StepParams& p, int64_t e,
-                                                 StepCounts& c) {
-  env.load(p.x, p.y, p.stride, e);
-  int prev = achieved_goals(env);
-  int steps = p.steps ? p.steps[e] : 0;
+struct GeneralSim {
+  Env& env;
+  __device__ __forceinline__ void load(const StepParams& p, int64_t e) { env.load(p.x, p.y, p.stride, e); }
+  __device__ __forceinline__ void store(const StepParams& p, int64_t e) { env.store(p.x, p.y, p.stride, e); }
+  __device__ __forceinline__ void load_initial() { env.load_initial(); }
+  __device__ __forceinline__ uint32_t do_step(int a) { return step(env, a); }
+  __device__ __forceinline__ int achieved() const { return achieved_goals(env); }
+  __device__ __forceinline__ int goals() const { return env.g(); }
+  static constexpr bool kCheapAchieved = false;
+};
+
+// `Sim` provides load / store / load_initial / do_step / achieved / goals.
+// kLean: the launch writes exactly reward[T][N] and terminated[T][N] (no step counter, no
+// truncation, no autoreset, no dgoals / moved / return_sum) -- the shape of a plain rollout --
+// so every optional output is compiled out of the loop.
+template <bool kLean, class Sim>
+__device__ __forceinline__ void run_steps_sim(Sim& sim, const StepParams& p, int64_t e,
+                                              StepCounts& c) {
+  int prev = sim.achieved();
+  int steps = (!kLean && p.steps) ? p.steps[e] : 0;
   float ret = 0.f;
-  const int g = env.g();
-  int a_next = p.actions[e];
-  for (int t = 0; t < p.T; ++t) {
-    const int64_t idx = (int64_t)t * p.N + e;
+  const int g = sim.goals();
+  const int64_t N = p.N;
+  const int T = p.T;
+  // lean launches have T * N < 2^32 (is_lean), so one 32-bit element offset addresses all arrays
+  const uint32_t n32 = (uint32_t)N;
+  uint32_t off = (uint32_t)e;
+  const uint8_t* __restrict__ actions = p.actions;
+  float* __restrict__ reward = p.reward;
+  uint8_t* __restrict__ terminated = p.terminated;
+  const float r_plain = c_reward_lut[kMaxObjects];  // -0.01f
+  int a_next = kLean ? actions[off] : actions[e];
+  for (int t = 0; t < T; ++t) {
     const int a = a_next;
-    if (t + 1 < p.T) a_next = p.actions[idx + p.N];  // prefetch: independent of the state
-    const uint32_t moved = step(env, a);
-    const int ach = moved ? achieved_goals(env) : prev;
+    if (kLean) {
+      if (t + 1 < T) a_next = actions[off + n32];  // prefetch: independent of the state
+    } else {
+      if (t + 1 < T) a_next = actions[(int64_t)(t + 1) * N + e];
+    }
+    const uint32_t moved = sim.do_step(a);
+    const int ach = Sim::kCheapAchieved ? sim.achieved() : (moved ? sim.achieved() : prev);
     const bool term = ach == g;  // puzzle.py:409-411
     const int dg = ach - prev;
     prev = ach;
-    ++steps;
     // gym_env.py:212-221; the float64 value (dg - 0.01) was rounded to float32 once, on the host
-    const float r = term ? 10.0f : c_reward_lut[dg + kMaxObjects];
-    const bool trunc = p.max_steps > 0 && steps >= p.max_steps;  // gym_env.py:223
-    if (p.reward) p.reward[idx] = r;
-    if (p.dgoals) p.dgoals[idx] = (int8_t)dg;
-    if (p.terminated) p.terminated[idx] = term ? 1 : 0;
-    if (p.truncated) p.truncated[idx] = trunc ? 1 : 0;
-    if (p.moved) p.moved[idx] = moved;
-    ret += r;
+    float r = r_plain;
+    if (dg != 0) r = c_reward_lut[dg + kMaxObjects];
+    r = term ? 10.0f : r;
     c.terminated += term ? 1u : 0u;
     c.moved += moved ? 1u : 0u;
     c.dgoals += dg > 0 ? (uint32_t)dg : 0u;
     c.invalid += (unsigned)a > 3u ? 1u : 0u;
-    if ((p.flags & kFlagAutoreset) && (term || trunc)) {
-      env.load_initial();
-      prev = achieved_goals(env);
-      steps = 0;
+    if (kLean) {
+      reward[off] = r;
+      terminated[off] = term ? 1 : 0;
+      off += n32;
+    } else {
+      const int64_t idx = (int64_t)t * N + e;
+      ++steps;
+      const bool trunc = p.max_steps > 0 && steps >= p.max_steps;  // gym_env.py:223
+      if (p.reward) p.reward[idx] = r;
+      if (p.dgoals) p.dgoals[idx] = (int8_t)dg;
+      if (p.terminated) p.terminated[idx] = term ? 1 : 0;
+      if (p.truncated) p.truncated[idx] = trunc ? 1 : 0;
+      if (p.moved) p.moved[idx] = moved;
+      ret += r;
+      if ((p.flags & kFlagAutoreset) && (term || trunc)) {
+        sim.load_initial();
+        prev = sim.achieved();
+        steps = 0;
+      }
     }
   }
-  env.store(p.x, p.y, p.stride, e);
-  if (p.steps) p.steps[e] = steps;
-  if (p.return_sum) p.return_sum[e] += ret;
+  sim.store(p, e);
+  if (!kLean) {
+    if (p.steps) p.steps[e] = steps;
+    if (p.return_sum) p.return_sum[e] += ret;
+  }
+}
+
+template <bool kLean, class Env>
+__device__ __forceinline__ void run_steps_thread(Env& env, const StepParams& p, int64_t e,
+                                                 StepCounts& c) {
+  GeneralSim<Env> sim{env};
+  sim.load(p, e);
+  run_steps_sim<kLean>(sim, p, e, c);
+}
+
+// true when a launch has the "plain rollout" output shape (see run_steps_sim)
+inline bool is_lean(const StepParams& p) {
+  return p.reward && p.terminated && !p.dgoals && !p.truncated && !p.moved && !p.steps &&
+         !p.return_sum && p.flags == 0 && p.max_steps <= 0 &&
+         (int64_t)p.T * p.N < ((int64_t)1 << 32);
 }
 
 }  // namespace pw

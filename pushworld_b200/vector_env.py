@@ -203,9 +203,11 @@ class PushWorldVectorEnv:
         return actions
 
     def rollout(self, actions: torch.Tensor, want_reward: bool = True, want_terminated: bool = True,
-                want_dgoals: bool = False, want_truncated: bool = False,
+                want_dgoals: bool = False, want_truncated: bool = False, want_return: bool = False,
                 out: Optional[RolloutOutput] = None) -> RolloutOutput:
-        """T fused steps in one launch; ``actions`` uint8 ``[T, N]`` on the device."""
+        """T fused steps in one launch; ``actions`` uint8 ``[T, N]`` on the device.  With only
+        reward + terminated requested and no ``max_steps`` / ``autoreset`` the engine runs its
+        lean rollout loop (every optional output compiled out)."""
         self._require_reset()
         if actions.dim() != 2:
             raise ValueError("actions must have shape [T, N]")
@@ -218,13 +220,17 @@ class PushWorldVectorEnv:
                 terminated=torch.empty((t, n), dtype=torch.uint8, device=dev) if want_terminated else None,
                 dgoals=torch.empty((t, n), dtype=torch.int8, device=dev) if want_dgoals else None,
                 truncated=torch.empty((t, n), dtype=torch.uint8, device=dev) if want_truncated else None,
-                return_sum=torch.zeros(n, dtype=torch.float32, device=dev),
+                return_sum=torch.zeros(n, dtype=torch.float32, device=dev) if want_return else None,
                 counters=torch.zeros(4, dtype=torch.int64, device=dev),
             )
+        track_steps = self.max_steps is not None or self.autoreset
         self.engine.rollout(self.xy, self._sel, actions, reward=out.reward, terminated=out.terminated,
-                            dgoals=out.dgoals, truncated=out.truncated, steps=self.steps,
+                            dgoals=out.dgoals, truncated=out.truncated,
+                            steps=self.steps if track_steps else None,
                             max_steps=self.max_steps, return_sum=out.return_sum,
                             counters=out.counters, autoreset=self.autoreset)
+        if not track_steps:
+            self.steps += actions.shape[0]
         return out
 
     # ------------------------------------------------------------------ host-buffer entry point
@@ -285,9 +291,12 @@ class _HostPipe:
                 self.s_run.wait_event(self.ev_in[b])
                 if k >= self.DEPTH:
                     self.s_run.wait_event(self.ev_out[b])  # outputs of chunk k-DEPTH copied out
+                track = env.max_steps is not None or env.autoreset
                 env.engine.rollout(env.xy, env._sel, self.d_act[b][:m], reward=self.d_rew[b][:m],
-                                   terminated=self.d_term[b][:m], steps=env.steps,
+                                   terminated=self.d_term[b][:m], steps=env.steps if track else None,
                                    max_steps=env.max_steps, autoreset=env.autoreset)
+                if not track:
+                    env.steps += m
                 self.ev_run[b].record(self.s_run)
             with torch.cuda.stream(self.s_out):
                 self.s_out.wait_event(self.ev_run[b])

@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <string.h>
 
+#include "pw_board.cuh"
 #include "pw_core.cuh"
 #include "pw_render_core.cuh"
 
@@ -69,6 +70,26 @@ struct HostPos {
 };
 
 extern "C" {
+
+// Same walk through the whole-grid bitboard rule (pw_board.cuh, NMAX = 8).  Returns -1 if the
+// puzzle does not fit one board, -2 if the start state is not regular.
+int hc_board_walk(const uint64_t* blob, int* x, int* y, const uint8_t* actions, int n_actions,
+                  int* xs, int* ys, uint32_t* moved, int* achieved) {
+  HostTable t{blob};
+  const int W = t.word(pw::kHdrDims) & 0xffff, H = t.word(pw::kHdrDims) >> 16;
+  const int n = t.word(pw::kHdrCounts) & 0xffff;
+  if (W * H > 64 || n > 8) return -1;
+  pw::Board<8> s;
+  pw::board_init(s, t);
+  if (!pw::board_load(s, t, [&](int k) { return x[k]; }, [&](int k) { return y[k]; })) return -2;
+  for (int i = 0; i < n_actions; ++i) {
+    moved[i] = pw::board_step(s, actions[i]);
+    achieved[i] = pw::board_achieved(s);
+    for (int k = 0; k < n; ++k)
+      pw::board_position(s.b[k], W, &xs[(size_t)i * n + k], &ys[(size_t)i * n + k]);
+  }
+  return n;
+}
 
 // Expands pw::cell_code() into a uint8 image [H*ppc][W*ppc][3] (the CUDA kernel does the same
 // expansion with shared-memory row patterns; this loop is deliberately the naive one).

@@ -59,3 +59,70 @@ def test_cell_code_matches_reference_renders(golden):
         assert list(img.shape) == case["shape"]
         assert hashlib.sha256(img.tobytes()).hexdigest() == case["sha256_u8"], (key, case["ppc"])
     assert len(renders["cases"]) > 100
+
+
+def test_bitboard_rule_matches_reference_vectors(golden):
+    """pw_board.cuh (whole-grid uint64 boards, used when width*height <= 64) on every golden
+    transition of every eligible puzzle, and against the general rule on random walks."""
+    eligible = 0
+    for key in golden.keys():
+        rec = golden.rec(key)
+        if rec["width"] * rec["height"] > 64 or rec["n"] > 8:
+            continue
+        parsed = tables.parse_puzzle(golden.text(key))
+        blob = tables.build_blob(parsed)
+        for tag in ("sol", "walk"):
+            if not golden.has(key, f"{tag}_actions"):
+                continue
+            actions = golden.arr(key, f"{tag}_actions")
+            ref = golden.arr(key, f"{tag}_states").astype(np.int32)
+            out = hostcheck.board_walk(blob, parsed.initial_state, actions)
+            regular = np.frombuffer(blob, np.uint32)[3] & tables.FLAG_REGULAR
+            if out is None:
+                assert not regular, key
+                continue
+            states, moved, ach = out
+            assert np.array_equal(states, ref[1:]), key
+            assert np.array_equal(ach, golden.arr(key, f"{tag}_achieved")[1:].astype(np.int32)), key
+            changed = (ref[1:] != ref[:-1]).any(axis=2)
+            bits = (moved[:, None] >> np.arange(ref.shape[1])[None, :]) & 1
+            assert np.array_equal(bits.astype(bool), changed), key
+        eligible += 1
+    assert eligible >= 10
+
+
+def test_bitboard_rule_equals_general_rule_on_random_small_puzzles():
+    """Random small puzzles (multi-cell shapes, chains, agent walls): bitboard == general rule,
+    including invalid actions."""
+    rng = np.random.default_rng(2026)
+    checked = 0
+    for trial in range(300):
+        w, h = int(rng.integers(3, 7)), int(rng.integers(2, 7))
+        if (w + 2) * (h + 2) > 64:
+            continue
+        grid = [["." for _ in range(w)] for _ in range(h)]
+        names = ["a"] + [f"m{k}" for k in range(int(rng.integers(1, 6)))]
+        for name in names:
+            for _ in range(int(rng.integers(1, 4))):  # a few cells each, maybe disconnected
+                x, y = int(rng.integers(w)), int(rng.integers(h))
+                if grid[y][x] == ".":
+                    grid[y][x] = name
+        for name in ("w", "aw", "g0"):
+            x, y = int(rng.integers(w)), int(rng.integers(h))
+            if grid[y][x] == ".":
+                grid[y][x] = name
+        text = "\n".join(" ".join(row) for row in grid) + "\n"
+        try:
+            parsed = tables.parse_puzzle(text)
+        except (ValueError, AssertionError):
+            continue
+        blob = tables.build_blob(parsed)
+        actions = rng.integers(0, 5, size=200).astype(np.uint8)  # 4 = invalid -> no-op
+        out = hostcheck.board_walk(blob, parsed.initial_state, actions)
+        if out is None:
+            continue
+        ref = hostcheck.walk(blob, parsed.initial_state, actions)
+        for got, want in zip(out, ref):
+            assert np.array_equal(got, want), text
+        checked += 1
+    assert checked > 100
