@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "../../include/pushworld_b200.h"
+#include "pw_board.cuh"
 #include "pw_core.cuh"
 #include "pw_host.h"
 #include "pw_internal.h"
@@ -80,9 +81,11 @@ int check_common(const PwEngine* e, int64_t n, const int32_t* puzzle_id, int puz
 #define PW_RETURN_IF_EMPTY(n) \
   if ((n) == 0) return PW_OK
 
-// bitboard kernel: the whole grid fits one uint64 and the puzzle starts in a regular state
-int board_eligible(const PuzzleInfo& info) {
-  return (info.width * info.height <= 64 && (info.flags & PW_TABLE_FLAG_REGULAR)) ? 1 : 0;
+// bitboard kernels (pw_board.cuh): the interior fits one machine word and the puzzle starts in a
+// regular state; returns the number of bits needed, 1 << 30 if not eligible
+int board_bits_of(const PuzzleInfo& info) {
+  if (!(info.flags & PW_TABLE_FLAG_REGULAR)) return 1 << 30;
+  return board_bits(info.width, info.height);
 }
 
 int n_limit_of(const PwEngine* e, const int32_t* puzzle_id, int puzzle_uniform) {
@@ -292,7 +295,7 @@ int pw_rollout(PwEngine* e, int64_t n_envs, int32_t n_steps, const int32_t* puzz
   p.puzzle_uniform = puzzle_id ? 0 : puzzle_uniform;
   p.uniform_u64 = puzzle_id ? 0 : e->puzzles[(size_t)puzzle_uniform].size_u64;
   p.n_max = e->n_max;
-  p.board_ok = puzzle_id ? 0 : board_eligible(e->puzzles[(size_t)puzzle_uniform]);
+  p.board_bits = puzzle_id ? (1 << 30) : board_bits_of(e->puzzles[(size_t)puzzle_uniform]);
   p.x = x;
   p.y = y;
   p.stride = stride;
@@ -333,7 +336,7 @@ int pw_step(PwEngine* e, int64_t n_envs, const int32_t* puzzle_id, int puzzle_un
   p.puzzle_uniform = puzzle_id ? 0 : puzzle_uniform;
   p.uniform_u64 = puzzle_id ? 0 : e->puzzles[(size_t)puzzle_uniform].size_u64;
   p.n_max = e->n_max;
-  p.board_ok = puzzle_id ? 0 : board_eligible(e->puzzles[(size_t)puzzle_uniform]);
+  p.board_bits = puzzle_id ? (1 << 30) : board_bits_of(e->puzzles[(size_t)puzzle_uniform]);
   p.x = x;
   p.y = y;
   p.stride = stride;
@@ -458,7 +461,7 @@ int pw_step_render(PwEngine* e, int64_t n_envs, const int32_t* puzzle_id, int pu
   p.puzzle_uniform = puzzle_id ? 0 : puzzle_uniform;
   p.uniform_u64 = puzzle_id ? 0 : e->puzzles[(size_t)puzzle_uniform].size_u64;
   p.n_max = e->n_max;
-  p.board_ok = puzzle_id ? 0 : board_eligible(e->puzzles[(size_t)puzzle_uniform]);
+  p.board_bits = puzzle_id ? (1 << 30) : board_bits_of(e->puzzles[(size_t)puzzle_uniform]);
   p.x = x;
   p.y = y;
   p.stride = stride;

@@ -1,21 +1,25 @@
-// pw_board.cuh -- whole-grid bitboard form of the transition rule (host/device code).
+// pw_board.cuh -- compact bitboard form of the transition rule (host/device code).
 //
-// For puzzles whose grid has at most 64 cells (width * height <= 64 incl. the wall border, e.g.
-// BASELINE config 2's `Road Block`, 8x5) every object is ONE uint64 occupancy board, cell (x, y)
-// at bit y * W + x, and a move is a shift by 1 (LEFT/RIGHT) or W (UP/DOWN) bits.
+// For small puzzles every object is ONE machine word of occupancy bits and a move is a shift.
+// Only the INTERIOR of the grid is stored (the 1-cell border is wall by construction,
+// puzzle.py:160-168): with pitch P = W - 1, interior cell (x, y), 1 <= x <= W-2, 1 <= y <= H-2,
+// lives at bit 1 + (y-1) * P + (x-1).  Column W-1 of every row (bit ... + P - 1) and bit 0 are
+// GUARD bits that are set in the wall board, so a horizontal move off either side of a row lands
+// on a wall bit; vertical moves off the first / last interior row are caught by an edge mask
+// instead of guard rows.  A board therefore needs 1 + (H-2) * (W-1) bits: 22 for BASELINE config
+// 2's `Road Block` (8x5) -> uint32 boards; up to 64 bits -> uint64 boards.
 //
-// The board form is only used for REGULAR states: every object inside the grid, no movable
+// The board form is only used for REGULAR states: every object inside the interior, no movable
 // overlapping another movable or a wall, the agent clear of aw UNION w.  Then
 //   * the "not already overlapping" terms of puzzle.py:562,592 are vacuous, so
-//       pushes(i, j)  <=>  shift(B_i) & B_j != 0          blocked(j, S)  <=>  shift(B_j) & S != 0
-//   * no object touches a border cell (the border is wall), so shifts never wrap around or fall
-//     off the 64-bit word, and
+//       pushes(i, j)  <=>  shift(B_i) & B_j != 0
+//       blocked(j, S) <=>  shift(B_j) & S != 0  or  B_j touches the edge row it moves off
 //   * a step maps regular states to regular states (anything a moved object would overlap is
 //     pushed along or stops the move), so the check is needed once, when the state is loaded.
 // With U = union of the shifted boards of the pushed set P, j joins P iff U & B_j != 0
-// (puzzle.py:359-382); the sweep below repeats until P stops growing.  Irregular states are
-// never handled here: board_load() reports them and the caller runs the general rule
-// (pw_core.cuh) for that environment instead.
+// (puzzle.py:359-382); sweeps repeat until P stops growing.  Irregular states are never handled
+// here: board_load() reports them and the caller runs the general rule (pw_core.cuh) for that
+// environment instead.
 #pragma once
 #include <stdint.h>
 
@@ -23,13 +27,17 @@
 
 namespace pw {
 
-template <int NMAX>
+template <int NMAX, typename Word>
 struct Board {
-  uint64_t b[NMAX];     // occupancy of object k (0 for k >= n)
-  uint64_t goal[NMAX];  // goal[k] = board of object k+1 sitting on its goal (~0 when none)
-  uint64_t wall, awall;
-  int W, n, g;
+  Word b[NMAX];              // occupancy of object k (0 for k >= n)
+  Word goal[NMAX];           // goal[k] = board of object k+1 sitting on its goal (all ones: none)
+  Word wall, awall;          // interior walls + guard bits; awall = aw UNION w
+  Word edge_up, edge_down;   // first / last interior row
+  int P, n, g;               // pitch = W - 1
 };
+
+// bits a puzzle needs in board form
+PW_HD int board_bits(int W, int H) { return (W < 3 || H < 3) ? 1 << 30 : 1 + (H - 2) * (W - 1); }
 
 PW_HD int pw_ctz64(uint64_t v) {
 #if defined(__CUDA_ARCH__)
@@ -39,60 +47,76 @@ PW_HD int pw_ctz64(uint64_t v) {
 #endif
 }
 
-// Places shape `d` at (x, y); returns false if it does not lie inside the grid.
-template <class Table>
-PW_HD bool place_shape(const Table& t, uint32_t d, int x, int y, int W, int H, uint64_t* out) {
+// interior part of a full-width grid row mask, as board bits of interior row r
+template <typename Word>
+PW_HD Word board_row(uint64_t grid_row, int r, int W) {
+  const uint64_t interior = (grid_row >> 1) & ((1ull << (W - 2)) - 1ull);
+  return (Word)(interior << (1 + r * (W - 1)));
+}
+
+// Places shape `d` at grid position (x, y); false if it does not lie inside the interior.
+template <typename Word, class Table>
+PW_HD bool place_shape(const Table& t, uint32_t d, int x, int y, int W, int H, Word* out) {
   const int w = desc_w(d), h = desc_h(d);
-  if (x < 0 || y < 0 || x + w > W || y + h > H) return false;
-  uint64_t board = 0;
+  if (x < 1 || y < 1 || x + w > W - 1 || y + h > H - 1) return false;
+  Word board = 0;
   const int o = desc_off(d);
-  for (int r = 0; r < h; ++r) board |= t.row(o + r) << ((y + r) * W + x);
+  for (int r = 0; r < h; ++r)
+    board |= (Word)((uint64_t)t.row(o + r) << (1 + (y - 1 + r) * (W - 1) + (x - 1)));
   *out = board;
   return true;
 }
 
-// Static part (walls, goal boards); valid when W * H <= 64 and n <= NMAX.
-template <int NMAX, class Table>
-PW_HD void board_init(Board<NMAX>& s, const Table& t) {
+// Static part (walls, guards, edges, goal boards); needs board_bits(W, H) <= bits of Word.
+template <int NMAX, typename Word, class Table>
+PW_HD void board_init(Board<NMAX, Word>& s, const Table& t) {
   const uint32_t dims = t.word(kHdrDims), counts = t.word(kHdrCounts);
   const int W = (int)(dims & 0xffffu), H = (int)(dims >> 16);
-  s.W = W;
+  const int P = W - 1;
+  s.P = P;
   s.n = (int)(counts & 0xffffu);
   s.g = (int)(counts >> 16);
   const int wo = (int)t.word(kHdrWallOff), ao = (int)t.word(kHdrAwallOff);
+  Word guard = 1;  // bit 0
   s.wall = s.awall = 0;
-  for (int y = 0; y < H; ++y) {
-    s.wall |= t.row(wo + y) << (y * W);
-    s.awall |= t.row(ao + y) << (y * W);
+  for (int r = 0; r < H - 2; ++r) {
+    guard |= (Word)((Word)1 << (1 + r * P + (P - 1)));
+    s.wall |= board_row<Word>(t.row(wo + r + 1), r, W);
+    s.awall |= board_row<Word>(t.row(ao + r + 1), r, W);
   }
+  s.wall |= guard;
+  s.awall |= guard;
+  const Word row_bits = (Word)((((uint64_t)1 << (W - 2)) - 1ull) << 1);
+  s.edge_up = row_bits;
+  s.edge_down = (Word)(row_bits << ((H - 3) * P));
   const int desc_word = (int)t.word(kHdrObjOff) * 2;
 #pragma unroll
   for (int k = 0; k < NMAX; ++k) {
     s.b[k] = 0;
-    s.goal[k] = ~0ull;
+    s.goal[k] = (Word) ~(Word)0;
     if (k + 1 < s.n && k < s.g) {
       const uint32_t gw = t.word(desc_word + 4 * (k + 1) + 2);
-      uint64_t board;
-      if (place_shape(t, t.word(desc_word + 4 * (k + 1)), lo16(gw), hi16(gw), W, H, &board))
-        s.goal[k] = board;  // a goal the object cannot reach inside the grid never matches
+      Word board;
+      if (place_shape<Word>(t, t.word(desc_word + 4 * (k + 1)), lo16(gw), hi16(gw), W, H, &board))
+        s.goal[k] = board;  // a goal the object cannot reach inside the interior never matches
     }
   }
 }
 
 // Builds the boards from positions; false if the state is not regular (see file comment).
-template <int NMAX, class Table, class GetX, class GetY>
-PW_HD bool board_load(Board<NMAX>& s, const Table& t, GetX get_x, GetY get_y) {
+template <int NMAX, typename Word, class Table, class GetX, class GetY>
+PW_HD bool board_load(Board<NMAX, Word>& s, const Table& t, GetX get_x, GetY get_y) {
   const uint32_t dims = t.word(kHdrDims);
   const int W = (int)(dims & 0xffffu), H = (int)(dims >> 16);
   const int desc_word = (int)t.word(kHdrObjOff) * 2;
-  uint64_t seen = 0;
+  Word seen = 0;
   bool ok = true;
 #pragma unroll
   for (int k = 0; k < NMAX; ++k) {
     s.b[k] = 0;
     if (k < s.n) {
-      uint64_t board = 0;
-      ok = ok && place_shape(t, t.word(desc_word + 4 * k), get_x(k), get_y(k), W, H, &board);
+      Word board = 0;
+      ok = ok && place_shape<Word>(t, t.word(desc_word + 4 * k), get_x(k), get_y(k), W, H, &board);
       ok = ok && (board & seen) == 0 && (board & (k == 0 ? s.awall : s.wall)) == 0;
       seen |= board;
       s.b[k] = board;
@@ -101,46 +125,56 @@ PW_HD bool board_load(Board<NMAX>& s, const Table& t, GetX get_x, GetY get_y) {
   return ok;
 }
 
-// Position (bbox-min corner) of a non-empty board.
-PW_HD void board_position(uint64_t board, int W, int* x, int* y) {
-  const int first = pw_ctz64(board);
-  *y = first / W;
+// Grid position (bbox-min corner) of a non-empty board with pitch P.
+template <typename Word>
+PW_HD void board_position(Word board, int P, int* x, int* y) {
+  const uint64_t v = (uint64_t)board >> 1;  // drop the guard bit 0
+  const int r = pw_ctz64(v) / P;
   uint64_t cols = 0;
-  const uint64_t row_mask = (W >= 64) ? ~0ull : ((1ull << W) - 1ull);
-  for (uint64_t v = board >> (*y * W); v; v >>= W) cols |= v & row_mask;
-  *x = pw_ctz64(cols);
+  const uint64_t row_mask = (1ull << P) - 1ull;
+  for (uint64_t rest = v >> (r * P); rest; rest >>= P) cols |= rest & row_mask;
+  *x = pw_ctz64(cols) + 1;
+  *y = r + 1;
+}
+
+// Per-action constants, looked up by action index (kept in shared memory by the kernels):
+// shift amounts (RIGHT / DOWN move towards higher bits, LEFT / UP towards lower bits,
+// puzzle.py:43-50) and the edge row a vertical move would leave the interior through.
+template <typename Word>
+struct alignas(16) BoardAction {
+  Word edge;
+  uint32_t sl, sr;
+};
+
+template <int NMAX, typename Word>
+PW_HD void board_action_table(const Board<NMAX, Word>& s, BoardAction<Word>* lut /*[4]*/) {
+  const uint32_t P = (uint32_t)s.P;
+  lut[0].sl = 0, lut[0].sr = 1, lut[0].edge = 0;            // LEFT
+  lut[1].sl = 1, lut[1].sr = 0, lut[1].edge = 0;            // RIGHT
+  lut[2].sl = 0, lut[2].sr = P, lut[2].edge = s.edge_up;    // UP
+  lut[3].sl = P, lut[3].sr = 0, lut[3].edge = s.edge_down;  // DOWN
 }
 
 // One transition on boards.  Returns the moved-object bitmask (0 = nothing moved).
 // Straight-line formulation: every board is shifted once up front (m[k]); a sweep adds m[j] to
 // the union U for every object U touches (re-testing an already pushed object is idempotent, so
 // no "already pushed" bookkeeping is needed) and sweeps repeat until the pushed set stops
-// growing.  Walls hit by any pushed object are accumulated and tested once at the end.
-PW_HD uint32_t pick_byte(uint32_t packed, uint32_t index) {  // byte `index` (0..3) of `packed`
-#if defined(__CUDA_ARCH__)
-  return __byte_perm(packed, 0u, index | 0x4440u);
-#else
-  return (packed >> (8u * index)) & 0xffu;
-#endif
-}
-
-template <int NMAX>
-PW_HD uint32_t board_step(Board<NMAX>& s, int action) {
+// growing.  Obstacles hit by any pushed object are accumulated and tested once at the end.
+template <int NMAX, typename Word>
+PW_HD uint32_t board_step(Board<NMAX, Word>& s, int action, const BoardAction<Word>* lut) {
   const uint32_t au = (uint32_t)action;
-  const uint32_t a2 = au & 3u;
-  const uint32_t W = (uint32_t)s.W;
-  // RIGHT / DOWN move towards higher bits, LEFT / UP towards lower bits (puzzle.py:43-50)
-  const uint32_t sl = pick_byte((1u << 8) | (W << 24), a2);
-  const uint32_t sr = pick_byte(1u | (W << 16), a2);
-  uint64_t m[NMAX], mw[NMAX];
+  const BoardAction<Word> act = lut[au & 3u];
+  const uint32_t sl = act.sl, sr = act.sr;
+  const Word edge = act.edge;
+  Word m[NMAX], stop[NMAX];
 #pragma unroll
   for (int k = 0; k < NMAX; ++k) {
-    m[k] = (s.b[k] << sl) >> sr;
-    mw[k] = m[k] & s.wall;
+    m[k] = (Word)((Word)(s.b[k] << sl) >> sr);
+    stop[k] = (Word)((m[k] & (k == 0 ? s.awall : s.wall)) | (s.b[k] & edge));
   }
-  uint64_t u = m[0], hit_wall = 0;
+  Word u = m[0], hit = 0;
   uint32_t pushed = 1u;
-  bool grow = au <= 3u && (m[0] & s.awall) == 0;  // puzzle.py:353-354
+  bool grow = au <= 3u && stop[0] == 0;  // puzzle.py:353-354
   const bool agent_ok = grow;
   while (grow) {
     const uint32_t before = pushed;
@@ -148,20 +182,20 @@ PW_HD uint32_t board_step(Board<NMAX>& s, int action) {
     for (int j = 1; j < NMAX; ++j) {
       if ((u & s.b[j]) != 0) {  // b[j] == 0 for j >= n
         u |= m[j];
-        hit_wall |= mw[j];  // transitive stopping, puzzle.py:376-379
+        hit |= stop[j];  // transitive stopping, puzzle.py:376-379
         pushed |= 1u << j;
       }
     }
     grow = pushed != before;
   }
-  pushed = (agent_ok && hit_wall == 0) ? pushed : 0u;
+  pushed = (agent_ok && hit == 0) ? pushed : 0u;
 #pragma unroll
   for (int k = 0; k < NMAX; ++k) s.b[k] = ((pushed >> k) & 1u) ? m[k] : s.b[k];
   return pushed;
 }
 
-template <int NMAX>
-PW_HD int board_achieved(const Board<NMAX>& s) {  // puzzle.py:396-407
+template <int NMAX, typename Word>
+PW_HD int board_achieved(const Board<NMAX, Word>& s) {  // puzzle.py:396-407
   int count = 0;
 #pragma unroll
   for (int k = 0; k + 1 < NMAX; ++k) count += (s.b[k + 1] == s.goal[k]) ? 1 : 0;

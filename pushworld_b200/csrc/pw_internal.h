@@ -16,7 +16,7 @@ struct StepParams {
   int32_t puzzle_uniform;
   int32_t uniform_u64;  // blob size of puzzle_uniform (u64 units)
   int32_t n_max;        // planes in x / y
-  int32_t board_ok;     // puzzle_uniform is regular with width*height <= 64: bitboard kernel
+  int32_t board_bits;   // bits puzzle_uniform needs in board form if it is regular, else 1 << 30
   int32_t* x;
   int32_t* y;
   int64_t stride;

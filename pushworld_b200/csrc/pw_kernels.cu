@@ -101,25 +101,27 @@ __global__ void __launch_bounds__(kBlock)
 // and / or work.  Environments whose loaded state is not regular take the general rule through
 // a non-inlined slow path (positions in local memory), so results are exact for any input.
 // ------------------------------------------------------------------------------------------
-// per-block static boards, computed once by a few threads
+// per-block static boards, computed once by thread 0
+template <typename Word>
 struct BoardStatic {
-  uint64_t wall, awall;
-  uint64_t goal[8];
-  uint64_t init[8];
-  int W, n, g;
+  Word wall, awall, edge_up, edge_down;
+  Word goal[8];
+  Word init[8];
+  BoardAction<Word> act[4];
+  int P, n, g;
 };
 
-template <int NMAX>
+template <int NMAX, typename Word>
 struct BoardSim {
   static constexpr bool kCheapAchieved = true;
-  Board<NMAX>& s;
-  const BoardStatic& st;
+  Board<NMAX, Word>& s;
+  const BoardStatic<Word>& st;
   __device__ __forceinline__ void store(const StepParams& p, int64_t e) {
 #pragma unroll
     for (int k = 0; k < NMAX; ++k)
       if (k < s.n) {
         int x, y;
-        board_position(s.b[k], s.W, &x, &y);
+        board_position<Word>(s.b[k], s.P, &x, &y);
         p.x[k * p.stride + e] = x;
         p.y[k * p.stride + e] = y;
       }
@@ -128,7 +130,7 @@ struct BoardSim {
 #pragma unroll
     for (int k = 0; k < NMAX; ++k) s.b[k] = st.init[k];
   }
-  __device__ __forceinline__ uint32_t do_step(int a) { return board_step(s, a); }
+  __device__ __forceinline__ uint32_t do_step(int a) { return board_step(s, a, st.act); }
   __device__ __forceinline__ int achieved() const { return board_achieved(s); }
   __device__ __forceinline__ int goals() const { return s.g; }
 };
@@ -140,26 +142,29 @@ __device__ __noinline__ void general_slow_path(const uint64_t* table, const Step
   run_steps_thread<false>(env, p, e, c);
 }
 
-template <int NMAX, int MIN_BLOCKS, bool kLean>
+template <int NMAX, typename Word, int MIN_BLOCKS, bool kLean>
 __global__ void __launch_bounds__(kBlock, MIN_BLOCKS)
     k_steps_board(const __grid_constant__ StepParams p) {
   extern __shared__ uint64_t smem[];
   __shared__ uint32_t s_counters[4];
-  __shared__ BoardStatic st;
+  __shared__ BoardStatic<Word> st;
   if (threadIdx.x < 4) s_counters[threadIdx.x] = 0;
   stage_table(smem, p.blob + p.puzzle_off[p.puzzle_uniform], p.uniform_u64);
   const SharedTable tbl{smem};
   if (threadIdx.x == 0) {
-    Board<NMAX> tmp;
+    Board<NMAX, Word> tmp;
     board_init(tmp, tbl);
     const int desc_word = (int)tbl.word(kHdrObjOff) * 2;
     board_load(tmp, tbl, [&](int k) { return lo16(tbl.word(desc_word + 4 * k + 1)); },
                [&](int k) { return hi16(tbl.word(desc_word + 4 * k + 1)); });
     st.wall = tmp.wall;
     st.awall = tmp.awall;
-    st.W = tmp.W;
+    st.edge_up = tmp.edge_up;
+    st.edge_down = tmp.edge_down;
+    st.P = tmp.P;
     st.n = tmp.n;
     st.g = tmp.g;
+    board_action_table(tmp, st.act);
     for (int k = 0; k < NMAX; ++k) {
       st.goal[k] = tmp.goal[k];
       st.init[k] = tmp.b[k];
@@ -169,10 +174,12 @@ __global__ void __launch_bounds__(kBlock, MIN_BLOCKS)
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   StepCounts c;
   if (e < p.N) {
-    Board<NMAX> s;
+    Board<NMAX, Word> s;
     s.wall = st.wall;
     s.awall = st.awall;
-    s.W = st.W;
+    s.edge_up = st.edge_up;
+    s.edge_down = st.edge_down;
+    s.P = st.P;
     s.n = st.n;
     s.g = st.g;
 #pragma unroll
@@ -180,7 +187,7 @@ __global__ void __launch_bounds__(kBlock, MIN_BLOCKS)
     const bool regular = board_load(s, tbl, [&](int k) { return p.x[k * p.stride + e]; },
                                     [&](int k) { return p.y[k * p.stride + e]; });
     if (regular) {
-      BoardSim<NMAX> sim{s, st};
+      BoardSim<NMAX, Word> sim{s, st};
       run_steps_sim<kLean>(sim, p, e, c);
     } else {
       general_slow_path(smem, p, e, c);
@@ -315,17 +322,35 @@ cudaError_t launch_steps(const StepParams& p, int n_limit, cudaStream_t stream) 
   } while (0)
   if (p.puzzle_id == nullptr) {
     const size_t tbl = (size_t)p.uniform_u64 * 8;
-    if (p.board_ok && n_limit <= 8) {  // exact-n instantiations of the bitboard kernel
-      switch (n_limit) {
-        case 1:
-        case 2: PW_GO(k_steps_board<2 COMMA 8, tbl); break;
-        case 3: PW_GO(k_steps_board<3 COMMA 8, tbl); break;
-        case 4: PW_GO(k_steps_board<4 COMMA 8, tbl); break;
-        case 5: PW_GO(k_steps_board<5 COMMA 8, tbl); break;
-        case 6: PW_GO(k_steps_board<6 COMMA 8, tbl); break;
-        case 7: PW_GO(k_steps_board<7 COMMA 6, tbl); break;
-        default: PW_GO(k_steps_board<8 COMMA 6, tbl); break;
+    if (p.board_bits <= 64 && n_limit <= 8) {
+      // bitboard kernels: uint32 / uint64 boards; lean rollouts get exact-n instantiations
+      const bool w32 = p.board_bits <= 32;
+#define PW_BOARD(NB, MINB)                                                                      \
+  do {                                                                                          \
+    if (w32)                                                                                    \
+      k_steps_board<NB, uint32_t, MINB, true><<<grid, kBlock, tbl, stream>>>(p);                \
+    else                                                                                        \
+      k_steps_board<NB, uint64_t, MINB, true><<<grid, kBlock, tbl, stream>>>(p);                \
+  } while (0)
+      if (lean) {
+        switch (n_limit) {
+          case 1:
+          case 2: PW_BOARD(2, 8); break;
+          case 3: PW_BOARD(3, 8); break;
+          case 4: PW_BOARD(4, 8); break;
+          case 5: PW_BOARD(5, 8); break;
+          case 6: PW_BOARD(6, 8); break;
+          case 7: PW_BOARD(7, 6); break;
+          default: PW_BOARD(8, 6); break;
+        }
+      } else if (n_limit <= 4) {
+        if (w32) k_steps_board<4, uint32_t, 8, false><<<grid, kBlock, tbl, stream>>>(p);
+        else k_steps_board<4, uint64_t, 8, false><<<grid, kBlock, tbl, stream>>>(p);
+      } else {
+        if (w32) k_steps_board<8, uint32_t, 6, false><<<grid, kBlock, tbl, stream>>>(p);
+        else k_steps_board<8, uint64_t, 6, false><<<grid, kBlock, tbl, stream>>>(p);
       }
+#undef PW_BOARD
     } else if (n_limit <= 4) {
       PW_GO(k_steps_uniform<4, tbl);
     } else if (n_limit <= 8) {

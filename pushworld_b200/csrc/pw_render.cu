@@ -77,7 +77,7 @@ __device__ __forceinline__ void copy_row(uint8_t* dst, const uint8_t* src, int b
 
 template <typename T, bool kFused>
 __global__ void __launch_bounds__(kRenderBlock) k_render(const RenderParams p, const StepParams sp) {
-  extern __shared__ uint64_t smem[];
+  extern __shared__ __align__(16) uint64_t smem[];
   const int64_t e = blockIdx.x;
   const int pid = p.puzzle_id ? p.puzzle_id[e] : p.puzzle_uniform;
   const uint64_t* g_tbl = p.blob + p.puzzle_off[pid];
@@ -89,7 +89,9 @@ __global__ void __launch_bounds__(kRenderBlock) k_render(const RenderParams p, c
   int* s_y = s_x + 32;
   const int row_bytes = p.out_w * 3 * (int)sizeof(T);
   const int row_pitch = (row_bytes + 15) & ~15;
-  uint8_t* s_pat = reinterpret_cast<uint8_t*>(s_y + 32);  // 4 patterns: 3 regions + zero row
+  // 4 patterns (3 region rows + a zero row), 16-byte aligned for the 128-bit copies
+  uint8_t* s_pat = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(s_y + 32) + 15) & ~static_cast<uintptr_t>(15));
 
   const int n_u64 = (int)__ldg(reinterpret_cast<const uint32_t*>(g_tbl) + kHdrSizeU64);
   for (int i = threadIdx.x; i < n_u64; i += blockDim.x) s_tbl[i] = __ldg(g_tbl + i);
@@ -177,7 +179,7 @@ cudaError_t launch_render(const RenderParams& p, const StepParams* fused_step, i
   const int elem = p.dtype == 1 ? 4 : 1;
   const size_t row_pitch = ((size_t)p.out_w * 3 * elem + 15) & ~(size_t)15;
   const size_t smem = (size_t)p.max_blob_u64 * 8 + (size_t)p.max_cells * 8 + 64 * sizeof(int) +
-                      4 * row_pitch;
+                      16 + 4 * row_pitch;
   if (smem > 227 * 1024) return cudaErrorInvalidValue;
   StepParams sp{};
   if (fused_step) sp = *fused_step;

@@ -68,10 +68,10 @@ __device__ __forceinline__ void run_steps_sim(Sim& sim, const StepParams& p, int
     float r = r_plain;
     if (dg != 0) r = c_reward_lut[dg + kMaxObjects];
     r = term ? 10.0f : r;
-    c.terminated += term ? 1u : 0u;
-    c.moved += moved ? 1u : 0u;
-    c.dgoals += dg > 0 ? (uint32_t)dg : 0u;
-    c.invalid += (unsigned)a > 3u ? 1u : 0u;
+    if (term) ++c.terminated;
+    if (moved) ++c.moved;
+    c.dgoals += (uint32_t)max(dg, 0);
+    if ((unsigned)a > 3u) ++c.invalid;
     if (kLean) {
       reward[off] = r;
       terminated[off] = term ? 1 : 0;

@@ -52,7 +52,7 @@ def walk(blob: bytes, state, actions):
     return np.stack([xs, ys], axis=-1), moved, ach
 
 
-def board_walk(blob: bytes, state, actions):
+def board_walk(blob: bytes, state, actions, word_bits: int = 64):
     """Bitboard rule; returns None when the puzzle/state is not board-eligible."""
     buf = np.frombuffer(blob, dtype=np.uint64).copy()
     n = len(state)
@@ -65,7 +65,7 @@ def board_walk(blob: bytes, state, actions):
     moved = np.zeros(T, np.uint32)
     ach = np.zeros(T, np.int32)
     p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
-    rc = lib().hc_board_walk(p(buf), p(x), p(y), p(acts), T, p(xs), p(ys), p(moved), p(ach))
+    rc = lib().hc_board_walk(p(buf), word_bits, p(x), p(y), p(acts), T, p(xs), p(ys), p(moved), p(ach))
     if rc < 0:
         return None
     return np.stack([xs, ys], axis=-1), moved, ach

@@ -69,26 +69,37 @@ struct HostPos {
   int y(int j) const { return py[j]; }
 };
 
-extern "C" {
-
-// Same walk through the whole-grid bitboard rule (pw_board.cuh, NMAX = 8).  Returns -1 if the
-// puzzle does not fit one board, -2 if the start state is not regular.
-int hc_board_walk(const uint64_t* blob, int* x, int* y, const uint8_t* actions, int n_actions,
-                  int* xs, int* ys, uint32_t* moved, int* achieved) {
+template <typename Word>
+static int board_walk(const uint64_t* blob, int* x, int* y, const uint8_t* actions, int n_actions,
+                      int* xs, int* ys, uint32_t* moved, int* achieved) {
   HostTable t{blob};
   const int W = t.word(pw::kHdrDims) & 0xffff, H = t.word(pw::kHdrDims) >> 16;
   const int n = t.word(pw::kHdrCounts) & 0xffff;
-  if (W * H > 64 || n > 8) return -1;
-  pw::Board<8> s;
+  if (pw::board_bits(W, H) > (int)sizeof(Word) * 8 || n > 8) return -1;
+  pw::Board<8, Word> s;
   pw::board_init(s, t);
   if (!pw::board_load(s, t, [&](int k) { return x[k]; }, [&](int k) { return y[k]; })) return -2;
+  pw::BoardAction<Word> lut[4];
+  pw::board_action_table(s, lut);
   for (int i = 0; i < n_actions; ++i) {
-    moved[i] = pw::board_step(s, actions[i]);
+    moved[i] = pw::board_step(s, actions[i], lut);
     achieved[i] = pw::board_achieved(s);
     for (int k = 0; k < n; ++k)
-      pw::board_position(s.b[k], W, &xs[(size_t)i * n + k], &ys[(size_t)i * n + k]);
+      pw::board_position<Word>(s.b[k], s.P, &xs[(size_t)i * n + k], &ys[(size_t)i * n + k]);
   }
   return n;
+}
+
+extern "C" {
+
+// Same walk through the compact bitboard rule (pw_board.cuh, NMAX = 8).  word_bits selects
+// uint32 / uint64 boards.  Returns -1 if the puzzle does not fit, -2 if the start state is not
+// regular.
+int hc_board_walk(const uint64_t* blob, int word_bits, int* x, int* y, const uint8_t* actions,
+                  int n_actions, int* xs, int* ys, uint32_t* moved, int* achieved) {
+  if (word_bits == 32)
+    return board_walk<uint32_t>(blob, x, y, actions, n_actions, xs, ys, moved, achieved);
+  return board_walk<uint64_t>(blob, x, y, actions, n_actions, xs, ys, moved, achieved);
 }
 
 // Expands pw::cell_code() into a uint8 image [H*ppc][W*ppc][3] (the CUDA kernel does the same

@@ -64,10 +64,11 @@ def test_cell_code_matches_reference_renders(golden):
 def test_bitboard_rule_matches_reference_vectors(golden):
     """pw_board.cuh (whole-grid uint64 boards, used when width*height <= 64) on every golden
     transition of every eligible puzzle, and against the general rule on random walks."""
-    eligible = 0
+    eligible = n32 = 0
     for key in golden.keys():
         rec = golden.rec(key)
-        if rec["width"] * rec["height"] > 64 or rec["n"] > 8:
+        bits = 1 + (rec["height"] - 2) * (rec["width"] - 1)
+        if bits > 64 or rec["n"] > 8:
             continue
         parsed = tables.parse_puzzle(golden.text(key))
         blob = tables.build_blob(parsed)
@@ -76,19 +77,24 @@ def test_bitboard_rule_matches_reference_vectors(golden):
                 continue
             actions = golden.arr(key, f"{tag}_actions")
             ref = golden.arr(key, f"{tag}_states").astype(np.int32)
-            out = hostcheck.board_walk(blob, parsed.initial_state, actions)
             regular = np.frombuffer(blob, np.uint32)[3] & tables.FLAG_REGULAR
-            if out is None:
+            outs = [hostcheck.board_walk(blob, parsed.initial_state, actions, 64)]
+            if bits <= 32:
+                outs.append(hostcheck.board_walk(blob, parsed.initial_state, actions, 32))
+                n32 += 1
+            if outs[0] is None:
                 assert not regular, key
                 continue
-            states, moved, ach = out
+            for other in outs[1:]:
+                assert all(np.array_equal(a, b) for a, b in zip(outs[0], other)), key
+            states, moved, ach = outs[0]
             assert np.array_equal(states, ref[1:]), key
             assert np.array_equal(ach, golden.arr(key, f"{tag}_achieved")[1:].astype(np.int32)), key
             changed = (ref[1:] != ref[:-1]).any(axis=2)
-            bits = (moved[:, None] >> np.arange(ref.shape[1])[None, :]) & 1
-            assert np.array_equal(bits.astype(bool), changed), key
+            mbits = (moved[:, None] >> np.arange(ref.shape[1])[None, :]) & 1
+            assert np.array_equal(mbits.astype(bool), changed), key
         eligible += 1
-    assert eligible >= 10
+    assert eligible >= 10 and n32 >= 5, (eligible, n32)
 
 
 def test_bitboard_rule_equals_general_rule_on_random_small_puzzles():
@@ -98,7 +104,8 @@ def test_bitboard_rule_equals_general_rule_on_random_small_puzzles():
     checked = 0
     for trial in range(300):
         w, h = int(rng.integers(3, 7)), int(rng.integers(2, 7))
-        if (w + 2) * (h + 2) > 64:
+        bits = 1 + h * (w + 1)
+        if bits > 64:
             continue
         grid = [["." for _ in range(w)] for _ in range(h)]
         names = ["a"] + [f"m{k}" for k in range(int(rng.integers(1, 6)))]
@@ -118,11 +125,14 @@ def test_bitboard_rule_equals_general_rule_on_random_small_puzzles():
             continue
         blob = tables.build_blob(parsed)
         actions = rng.integers(0, 5, size=200).astype(np.uint8)  # 4 = invalid -> no-op
-        out = hostcheck.board_walk(blob, parsed.initial_state, actions)
-        if out is None:
-            continue
         ref = hostcheck.walk(blob, parsed.initial_state, actions)
-        for got, want in zip(out, ref):
-            assert np.array_equal(got, want), text
-        checked += 1
+        for word_bits in (32, 64):
+            if bits > word_bits:
+                continue
+            out = hostcheck.board_walk(blob, parsed.initial_state, actions, word_bits)
+            if out is None:
+                continue
+            for got, want in zip(out, ref):
+                assert np.array_equal(got, want), text
+            checked += 1
     assert checked > 100
