@@ -59,15 +59,22 @@ class ClockSampler:
 
     def __init__(self, gpu_index: int):
         self.gpu = gpu_index
-        self.rows = []
+        self.rows = []  # (arrival time, csv line)
         self.proc = None
         self.thread = None
+        self.t_begin = self.t_end = None
+
+    def mark_begin(self):
+        self.t_begin = time.time()
+
+    def mark_end(self):
+        self.t_end = time.time()
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                 "-lms", "100", "-i", str(self.gpu)],
+                 "-lms", "20", "-i", str(self.gpu)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
@@ -77,7 +84,7 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.time(), line.strip()))
 
     def stop(self) -> dict:
         if self.proc is None:
@@ -89,7 +96,12 @@ class ClockSampler:
             self.proc.kill()
         sm, sm_max, power, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for row in self.rows:
+        inside = [r for t, r in self.rows
+                  if self.t_begin is not None and self.t_begin <= t <= (self.t_end or t) + 0.05]
+        window = "timed region"
+        if len(inside) < 3:  # very short timed region: use everything since the warm-up started
+            inside, window = [r for _, r in self.rows], "warm-up + timed region"
+        for row in inside:
             parts = [p.strip() for p in row.split(",")]
             if len(parts) < 9:
                 continue
@@ -107,6 +119,7 @@ class ClockSampler:
             "sm_max_mhz": max(sm_max) if sm_max else None,
             "power_w_max": max(power) if power else None,
             "samples": len(sm),
+            "window": window,
             "reasons": sorted(reasons),
         }
 
@@ -238,20 +251,21 @@ def run_ours(args) -> None:
         if ev1 is not None:
             ev1.record()
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for _ in range(args.warmup):
         one_step()
     torch.cuda.synchronize()
 
     # ---- timed region: device-resident inputs ------------------------------------------
     out.counters.zero_()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     kernel_events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
                      for _ in range(args.steps)]
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     distributed.barrier()
     torch.cuda.synchronize()
+    sampler.mark_begin()
     start.record()
     for k in range(args.steps):
         one_step(*kernel_events[k])
@@ -259,6 +273,7 @@ def run_ours(args) -> None:
     distributed.allreduce_counters(totals)  # the path's single collective (NCCL, int64[4])
     stop.record()
     torch.cuda.synchronize()
+    sampler.mark_end()
     distributed.barrier()
     clocks = sampler.stop() if rank == 0 else None
     elapsed_ms = distributed.max_over_ranks(start.elapsed_time(stop), dev)
@@ -272,7 +287,7 @@ def run_ours(args) -> None:
     h_act.copy_(actions)
     h_rew = torch.empty((T_STEPS, N_ENVS), dtype=torch.float32).pin_memory()
     h_term = torch.empty((T_STEPS, N_ENVS), dtype=torch.uint8).pin_memory()
-    e2e_steps = args.steps
+    e2e_steps = min(args.steps, 40)  # ~25 ms each (PCIe bound)
 
     def e2e_step():
         env.reset()
@@ -312,7 +327,7 @@ def run_ours(args) -> None:
     achieved = units * fused_bpu / (kernel_ms * 1e-3) / 1e9
     roofline = {
         "bound": "hbm",
-        "kernel": "k_steps_uniform (pw_rollout)",
+        "kernel": "k_steps_board<3, uint32_t> (pw_rollout)",
         "achieved": achieved,
         "peak": peak,
         "unit": "GB/s",
@@ -375,8 +390,8 @@ def run_ours(args) -> None:
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

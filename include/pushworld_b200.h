@@ -164,6 +164,14 @@ PW_API int pw_rollout(PwEngine* engine, int64_t n_envs, int32_t n_steps, const i
                uint8_t* truncated, int32_t* steps, int32_t max_steps, float* return_sum,
                uint64_t* counters, uint32_t flags, void* stream);
 
+/* Goal predicates of every environment's CURRENT state.
+ * Replaces: PushWorldPuzzle.count_achieved_goals (puzzle.py:396-407) and is_goal_state
+ * (puzzle.py:409-411) / satisfiesGoal (cpp/src/pushworld_puzzle.cc:462-469).
+ *   achieved[N] int32 (nullable)      is_goal[N] uint8 (nullable) */
+PW_API int pw_goals(PwEngine* engine, int64_t n_envs, const int32_t* puzzle_id, int puzzle_uniform,
+                    const int32_t* x, const int32_t* y, int64_t stride, int32_t* achieved,
+                    uint8_t* is_goal, void* stream);
+
 /* Successor expansion: for each of N states, the 4 successors (LEFT, RIGHT, UP, DOWN).
  * Successor s = a * N + e: x_out[j * stride_out + s] etc. (stride_out >= 4N).
  * Replaces: the 4 x getNextState + satisfiesGoal calls per node of best_first_search

@@ -357,6 +357,30 @@ int pw_step(PwEngine* e, int64_t n_envs, const int32_t* puzzle_id, int puzzle_un
   return err == cudaSuccess ? PW_OK : cuda_error(err, "pw_step");
 }
 
+int pw_goals(PwEngine* e, int64_t n_envs, const int32_t* puzzle_id, int puzzle_uniform,
+             const int32_t* x, const int32_t* y, int64_t stride, int32_t* achieved, uint8_t* is_goal,
+             void* stream) {
+  clear_error();
+  const int rc = check_common(e, n_envs, puzzle_id, puzzle_uniform, stride, n_envs);
+  if (rc != PW_OK) return rc;
+  PW_RETURN_IF_EMPTY(n_envs);
+  if (x == nullptr || y == nullptr) return set_error(PW_E_INVALID, "x / y is NULL");
+  DeviceGuard guard(e->device);
+  GoalParams p{};
+  p.blob = e->d_blob;
+  p.puzzle_off = e->d_off;
+  p.N = n_envs;
+  p.puzzle_id = puzzle_id;
+  p.puzzle_uniform = puzzle_id ? 0 : puzzle_uniform;
+  p.x = x;
+  p.y = y;
+  p.stride = stride;
+  p.achieved = achieved;
+  p.is_goal = is_goal;
+  const cudaError_t err = launch_goals(p, static_cast<cudaStream_t>(stream));
+  return err == cudaSuccess ? PW_OK : cuda_error(err, "pw_goals");
+}
+
 int pw_expand(PwEngine* e, int64_t n_states, const int32_t* puzzle_id, int puzzle_uniform,
               const int32_t* x_in, const int32_t* y_in, int64_t stride_in, int32_t* x_out,
               int32_t* y_out, int64_t stride_out, uint32_t* moved, uint8_t* goal, void* stream) {

@@ -66,6 +66,19 @@ struct ResetParams {
   const uint8_t* reset_mask;
 };
 
+struct GoalParams {
+  const uint64_t* blob;
+  const uint32_t* puzzle_off;
+  int64_t N;
+  const int32_t* puzzle_id;
+  int32_t puzzle_uniform;
+  const int32_t* x;
+  const int32_t* y;
+  int64_t stride;
+  int32_t* achieved;
+  uint8_t* is_goal;
+};
+
 struct RenderParams {
   const uint64_t* blob;
   const uint32_t* puzzle_off;
@@ -91,6 +104,7 @@ cudaError_t configure_render_kernels();
 cudaError_t launch_steps(const StepParams& p, int n_limit, cudaStream_t stream);
 cudaError_t launch_expand(const ExpandParams& p, int n_limit, cudaStream_t stream);
 cudaError_t launch_reset(const ResetParams& p, cudaStream_t stream);
+cudaError_t launch_goals(const GoalParams& p, cudaStream_t stream);
 cudaError_t launch_render(const RenderParams& p, const StepParams* fused_step, int n_limit,
                           cudaStream_t stream);
 cudaError_t upload_palette(const uint8_t* rgb, const float* rgb_f32, int n_colors);

@@ -301,6 +301,23 @@ __global__ void __launch_bounds__(kBlock) k_reset(const ResetParams p) {
   if (p.steps) p.steps[e] = 0;
 }
 
+// count_achieved_goals / is_goal_state of the current states (puzzle.py:396-411)
+__global__ void __launch_bounds__(kBlock) k_goals(const GoalParams p) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= p.N) return;
+  const int pid = p.puzzle_id ? p.puzzle_id[e] : p.puzzle_uniform;
+  const GlobalTable t{p.blob + p.puzzle_off[pid]};
+  const int g = (int)(t.word(kHdrCounts) >> 16);
+  const int desc_word = (int)t.word(kHdrObjOff) * 2;
+  int count = 0;
+  for (int k = 0; k < g; ++k) {
+    const uint32_t goal = t.word(desc_word + 4 * (k + 1) + 2);
+    count += (p.x[(k + 1) * p.stride + e] == lo16(goal) && p.y[(k + 1) * p.stride + e] == hi16(goal));
+  }
+  if (p.achieved) p.achieved[e] = count;
+  if (p.is_goal) p.is_goal[e] = count == g ? 1 : 0;
+}
+
 inline unsigned grid_for(int64_t n) { return (unsigned)((n + kBlock - 1) / kBlock); }
 
 }  // namespace
@@ -399,6 +416,12 @@ cudaError_t launch_expand(const ExpandParams& p, int n_limit, cudaStream_t strea
 cudaError_t launch_reset(const ResetParams& p, cudaStream_t stream) {
   if (p.N == 0) return cudaSuccess;
   k_reset<<<grid_for(p.N), kBlock, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_goals(const GoalParams& p, cudaStream_t stream) {
+  if (p.N == 0) return cudaSuccess;
+  k_goals<<<grid_for(p.N), kBlock, 0, stream>>>(p);
   return cudaGetLastError();
 }
 

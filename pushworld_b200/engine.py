@@ -193,6 +193,19 @@ class Engine:
                                  self._stream())
         )
 
+    def goals(self, xy: torch.Tensor, puzzle: PuzzleSel):
+        """(achieved int32 [N], is_goal uint8 [N]) of the current states
+        (count_achieved_goals / is_goal_state, puzzle.py:396-411)."""
+        n = self._chk_state(xy)
+        pid_ptr, pid = self._sel(puzzle, n)
+        achieved = torch.empty(n, dtype=torch.int32, device=self.device)
+        is_goal = torch.empty(n, dtype=torch.uint8, device=self.device)
+        _lib.check(
+            self._lib.pw_goals(self._h, n, pid_ptr, pid, xy[0].data_ptr(), xy[1].data_ptr(), n,
+                               achieved.data_ptr(), is_goal.data_ptr(), self._stream())
+        )
+        return achieved, is_goal
+
     def expand(self, xy: torch.Tensor, puzzle: PuzzleSel, xy_out: Optional[torch.Tensor] = None,
                moved: Optional[torch.Tensor] = None, goal: Optional[torch.Tensor] = None):
         """4 successors per state: returns (xy_out [2, n_max, 4N], moved int32 [4N], goal uint8
