@@ -82,15 +82,6 @@ PW_HD bool shapes_overlap(const Env& env, uint32_t di, uint32_t dj, int sx, int 
   return acc != 0;
 }
 
-// puzzle.py:567-593 evaluated directly: would i, moving by (dx, dy), push j?
-template <class Env>
-PW_HD bool pushes(const Env& env, uint32_t di, int xi, int yi, uint32_t dj, int xj, int yj,
-                  int dx, int dy) {
-  const int rx = xj - xi, ry = yj - yi;
-  if (!shapes_overlap(env, di, dj, rx - dx, ry - dy)) return false;
-  return !shapes_overlap(env, di, dj, rx, ry);
-}
-
 // puzzle.py:522-564 evaluated directly: is the object stopped by the static rows at `soff`?
 template <class Env>
 PW_HD bool static_blocked(const Env& env, uint32_t dj, int x, int y, int dx, int dy, int soff) {
@@ -118,6 +109,13 @@ PW_HD bool static_blocked(const Env& env, uint32_t dj, int x, int y, int dx, int
 // `Env` provides: n(), width(), height(), wall_off(), awall_off(), row(off), desc(j),
 // x(j), y(j), and the *_dyn(j) variants for a runtime index, translate(mask, dx, dy),
 // plus kStaticN (compile-time loop bound, 0 = use n()).
+//
+// For every pusher i the not-yet-pushed objects are handled in two phases so that the lanes of
+// a warp (one environment each) stay converged:
+//   1. a cheap bounding-box test of the MOVED pusher against every candidate j -> bit mask;
+//   2. only for the (few) candidates the exact row-mask tests and the wall test of the pushee.
+// Without the split, lanes whose pushes happen at different j would each execute the heavy
+// path on their own.
 template <class Env>
 PW_HD uint32_t step(Env& env, int action) {
   if ((unsigned)action > 3u) return 0;  // invalid actions are no-ops (counted by the caller)
@@ -131,14 +129,28 @@ PW_HD uint32_t step(Env& env, int action) {
     const int i = pw_ffs(frontier) - 1;
     frontier &= frontier - 1;
     const uint32_t di = env.desc_dyn(i);
-    const int xi = env.x_dyn(i), yi = env.y_dyn(i);
+    const int xm = env.x_dyn(i) + dx, ym = env.y_dyn(i) + dy;  // origin of the moved pusher
+    const int wi = desc_w(di), hi = desc_h(di);
+    // phase 1: -w_j < x_j - xm < w_i  and  -h_j < y_j - ym < h_i, as two unsigned range checks
+    uint32_t cand = 0;
 #pragma unroll
     for (int j = 1; j < jend; ++j) {
       if (Env::kStaticN && j >= n) break;
-      if ((pushed >> j) & 1u) continue;
       const uint32_t dj = env.desc(j);
-      const int xj = env.x(j), yj = env.y(j);
-      if (!pushes(env, di, xi, yi, dj, xj, yj, dx, dy)) continue;
+      const int wj1 = desc_w(dj) - 1, hj1 = desc_h(dj) - 1;
+      const bool near_x = (unsigned)(env.x(j) - xm + wj1) < (unsigned)(wi + wj1);
+      const bool near_y = (unsigned)(env.y(j) - ym + hj1) < (unsigned)(hi + hj1);
+      cand |= (near_x && near_y) ? (1u << j) : 0u;
+    }
+    cand &= ~pushed;
+    // phase 2: exact tests for the candidates
+    while (cand) {
+      const int j = pw_ffs(cand) - 1;
+      cand &= cand - 1;
+      const uint32_t dj = env.desc_dyn(j);
+      const int xj = env.x_dyn(j), yj = env.y_dyn(j);
+      if (!shapes_overlap(env, di, dj, xj - xm, yj - ym)) continue;            // would not touch
+      if (shapes_overlap(env, di, dj, xj - xm + dx, yj - ym + dy)) continue;   // already overlapping
       if (static_blocked(env, dj, xj, yj, dx, dy, env.wall_off())) return 0;
       pushed |= 1u << j;
       frontier |= 1u << j;

@@ -59,47 +59,80 @@ struct Elem<float> {
   static __device__ __forceinline__ float get(uint32_t pal, int c) { return c_pal_f32[pal][c]; }
 };
 
-// Copies `bytes` from shared `src` to global `dst` (same alignment class decided by caller).
+// One output row: `bytes` from shared `src` to global `dst`, by ONE warp (lanes over chunks).
 template <int VEC>
-__device__ __forceinline__ void copy_row(uint8_t* dst, const uint8_t* src, int bytes) {
+__device__ __forceinline__ void copy_row(uint8_t* dst, const uint8_t* src, int bytes, int lane) {
   if (VEC == 16) {
     const int n = bytes >> 4;
-    for (int i = threadIdx.x; i < n; i += blockDim.x)
+    for (int i = lane; i < n; i += 32)
       reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(src)[i];
   } else if (VEC == 4) {
     const int n = bytes >> 2;
-    for (int i = threadIdx.x; i < n; i += blockDim.x)
+    for (int i = lane; i < n; i += 32)
       reinterpret_cast<uint32_t*>(dst)[i] = reinterpret_cast<const uint32_t*>(src)[i];
   } else {
-    for (int i = threadIdx.x; i < bytes; i += blockDim.x) dst[i] = src[i];
+    for (int i = lane; i < bytes; i += 32) dst[i] = src[i];
   }
+}
+
+template <typename T>
+__device__ __forceinline__ void put_pixel(T* dst, uint32_t pal, const float4* s_pal_f, const uint32_t* s_pal_u);
+template <>
+__device__ __forceinline__ void put_pixel<float>(float* dst, uint32_t pal, const float4* s_pal_f,
+                                                 const uint32_t*) {
+  const float4 c = s_pal_f[pal];
+  dst[0] = c.x;
+  dst[1] = c.y;
+  dst[2] = c.z;
+}
+template <>
+__device__ __forceinline__ void put_pixel<uint8_t>(uint8_t* dst, uint32_t pal, const float4*,
+                                                   const uint32_t* s_pal_u) {
+  const uint32_t c = s_pal_u[pal];
+  dst[0] = (uint8_t)(c & 0xffu);
+  dst[1] = (uint8_t)((c >> 8) & 0xffu);
+  dst[2] = (uint8_t)((c >> 16) & 0xffu);
 }
 
 template <typename T, bool kFused>
 __global__ void __launch_bounds__(kRenderBlock) k_render(const RenderParams p, const StepParams sp) {
   extern __shared__ __align__(16) uint64_t smem[];
+  __shared__ float4 s_pal_f[16];
+  __shared__ uint32_t s_pal_u[16];
   const int64_t e = blockIdx.x;
   const int pid = p.puzzle_id ? p.puzzle_id[e] : p.puzzle_uniform;
   const uint64_t* g_tbl = p.blob + p.puzzle_off[pid];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
 
   // ---- shared memory carve-up -----------------------------------------------------------
-  uint64_t* s_tbl = smem;                          // max_blob_u64
-  uint64_t* s_code = s_tbl + p.max_blob_u64;       // max_cells
-  int* s_x = reinterpret_cast<int*>(s_code + p.max_cells);  // n_max (padded to 32)
+  uint64_t* s_tbl = smem;                                   // max_blob_u64
+  uint64_t* s_code = s_tbl + p.max_blob_u64;                // max_cells
+  int* s_x = reinterpret_cast<int*>(s_code + p.max_cells);  // 32 ints
   int* s_y = s_x + 32;
+  uint16_t* s_xmap = reinterpret_cast<uint16_t*>(s_y + 32);  // out_w entries: cx << 2 | region
   const int row_bytes = p.out_w * 3 * (int)sizeof(T);
   const int row_pitch = (row_bytes + 15) & ~15;
-  // 4 patterns (3 region rows + a zero row), 16-byte aligned for the 128-bit copies
+  // 2 pattern sets (double buffered) x 3 region rows, then a zero row; 16-byte aligned
   uint8_t* s_pat = reinterpret_cast<uint8_t*>(
-      (reinterpret_cast<uintptr_t>(s_y + 32) + 15) & ~static_cast<uintptr_t>(15));
+      (reinterpret_cast<uintptr_t>(s_xmap + p.out_w) + 15) & ~static_cast<uintptr_t>(15));
+  uint8_t* s_zero = s_pat + 6 * row_pitch;
 
   const int n_u64 = (int)__ldg(reinterpret_cast<const uint32_t*>(g_tbl) + kHdrSizeU64);
   for (int i = threadIdx.x; i < n_u64; i += blockDim.x) s_tbl[i] = __ldg(g_tbl + i);
+  if (threadIdx.x < 16) {
+    s_pal_f[threadIdx.x] = make_float4(c_pal_f32[threadIdx.x][0], c_pal_f32[threadIdx.x][1],
+                                       c_pal_f32[threadIdx.x][2], 0.f);
+    s_pal_u[threadIdx.x] = (uint32_t)c_pal_u8[threadIdx.x][0] | ((uint32_t)c_pal_u8[threadIdx.x][1] << 8) |
+                           ((uint32_t)c_pal_u8[threadIdx.x][2] << 16);
+  }
   __syncthreads();
   const SharedTable tbl{s_tbl};
   const uint32_t dims = tbl.word(kHdrDims);
   const int W = (int)(dims & 0xffffu), H = (int)(dims >> 16);
   const int n = (int)(tbl.word(kHdrCounts) & 0xffffu);
+  const int ppc = p.ppc, bw = p.bw;
+  const int img_h = H * ppc, img_w = W * ppc;
+  const int pad_top = (p.out_h - img_h) / 2, pad_left = (p.out_w - img_w) / 2;  // env_utils.py:81-82
 
   // ---- state (and the fused step) -----------------------------------------------------
   if (kFused) {
@@ -116,6 +149,18 @@ __global__ void __launch_bounds__(kRenderBlock) k_render(const RenderParams p, c
       s_y[j] = p.y[j * p.stride + e];
     }
   }
+  // pixel column -> (cell column, region) map, shared by every cell row of the frame
+  for (int X = threadIdx.x; X < p.out_w; X += blockDim.x) {
+    const int xi = X - pad_left;
+    uint16_t m = 0xffffu;  // zero padding
+    if (xi >= 0 && xi < img_w) {
+      const int cx = xi / ppc;
+      m = (uint16_t)((cx << 2) | region_of(xi - cx * ppc, ppc, bw));
+    }
+    s_xmap[X] = m;
+  }
+  for (int i = threadIdx.x; i < (row_pitch >> 2); i += blockDim.x)
+    reinterpret_cast<uint32_t*>(s_zero)[i] = 0u;
   __syncthreads();
 
   // ---- 1. cell codes --------------------------------------------------------------------
@@ -124,48 +169,40 @@ __global__ void __launch_bounds__(kRenderBlock) k_render(const RenderParams p, c
     const int cy = c / W, cx = c - cy * W;
     s_code[c] = cell_code(tbl, pos, cx, cy);
   }
-  // zero pattern (index 3)
-  for (int i = threadIdx.x; i < (row_pitch >> 2); i += blockDim.x)
-    reinterpret_cast<uint32_t*>(s_pat + 3 * row_pitch)[i] = 0u;
-  __syncthreads();
 
   // ---- 2. pixel rows --------------------------------------------------------------------
-  const int ppc = p.ppc, bw = p.bw;
-  const int img_h = H * ppc, img_w = W * ppc;
-  const int pad_top = (p.out_h - img_h) / 2, pad_left = (p.out_w - img_w) / 2;  // env_utils.py:81-82
   uint8_t* frame = static_cast<uint8_t*>(p.out) + (size_t)e * (size_t)p.out_h * (size_t)row_bytes;
   const bool vec16 = (row_bytes & 15) == 0 && (reinterpret_cast<uintptr_t>(frame) & 15) == 0;
   const bool vec4 = (row_bytes & 3) == 0 && (reinterpret_cast<uintptr_t>(frame) & 3) == 0;
-
-  auto emit = [&](int Y, const uint8_t* src) {
+  auto emit = [&](int Y, const uint8_t* src) {  // one warp writes one output row
     uint8_t* dst = frame + (size_t)Y * (size_t)row_bytes;
-    if (vec16) copy_row<16>(dst, src, row_bytes);
-    else if (vec4) copy_row<4>(dst, src, row_bytes);
-    else copy_row<1>(dst, src, row_bytes);
+    if (vec16) copy_row<16>(dst, src, row_bytes, lane);
+    else if (vec4) copy_row<4>(dst, src, row_bytes, lane);
+    else copy_row<1>(dst, src, row_bytes, lane);
   };
-
-  for (int Y = 0; Y < pad_top; ++Y) emit(Y, s_pat + 3 * row_pitch);
-  for (int Y = pad_top + img_h; Y < p.out_h; ++Y) emit(Y, s_pat + 3 * row_pitch);
-
-  for (int cy = 0; cy < H; ++cy) {
-    // build the three patterns of this cell row: element (rr, X, channel)
+  // builds the 3 region-row patterns of cell row cy into pattern set `buf`
+  auto build = [&](int cy, int buf) {
+    uint8_t* set = s_pat + buf * 3 * row_pitch;
     for (int i = threadIdx.x; i < 3 * p.out_w; i += blockDim.x) {
       const int rr = i / p.out_w, X = i - rr * p.out_w;
-      const int xi = X - pad_left;
+      const uint32_t m = s_xmap[X];
       uint32_t pal = kPalPad;
-      if (xi >= 0 && xi < img_w) {
-        const int cx = xi / ppc, ox = xi - cx * ppc;
-        const int rc = region_of(ox, ppc, bw);
-        pal = (uint32_t)(s_code[cy * W + cx] >> (4 * (rr * 3 + rc))) & 15u;
-      }
-      T* dst = reinterpret_cast<T*>(s_pat + rr * row_pitch) + 3 * X;
-      dst[0] = Elem<T>::get(pal, 0);
-      dst[1] = Elem<T>::get(pal, 1);
-      dst[2] = Elem<T>::get(pal, 2);
+      if (m != 0xffffu) pal = (uint32_t)(s_code[cy * W + (m >> 2)] >> (4 * (rr * 3 + (m & 3u)))) & 15u;
+      put_pixel<T>(reinterpret_cast<T*>(set + rr * row_pitch) + 3 * X, pal, s_pal_f, s_pal_u);
     }
-    __syncthreads();
+  };
+
+  __syncthreads();  // codes + zero row ready
+  for (int Y = warp; Y < pad_top; Y += n_warps) emit(Y, s_zero);
+  for (int Y = pad_top + img_h + warp; Y < p.out_h; Y += n_warps) emit(Y, s_zero);
+  build(0, 0);
+  __syncthreads();
+  for (int cy = 0; cy < H; ++cy) {
+    if (cy + 1 < H) build(cy + 1, (cy + 1) & 1);  // next cell row while this one streams out
+    const uint8_t* set = s_pat + (cy & 1) * 3 * row_pitch;
     const int Y0 = pad_top + cy * ppc;
-    for (int oy = 0; oy < ppc; ++oy) emit(Y0 + oy, s_pat + region_of(oy, ppc, bw) * row_pitch);
+    for (int oy = warp; oy < ppc; oy += n_warps)
+      emit(Y0 + oy, set + region_of(oy, ppc, bw) * row_pitch);
     __syncthreads();
   }
 }
@@ -179,7 +216,7 @@ cudaError_t launch_render(const RenderParams& p, const StepParams* fused_step, i
   const int elem = p.dtype == 1 ? 4 : 1;
   const size_t row_pitch = ((size_t)p.out_w * 3 * elem + 15) & ~(size_t)15;
   const size_t smem = (size_t)p.max_blob_u64 * 8 + (size_t)p.max_cells * 8 + 64 * sizeof(int) +
-                      16 + 4 * row_pitch;
+                      (size_t)p.out_w * 2 + 16 + 7 * row_pitch;
   if (smem > 227 * 1024) return cudaErrorInvalidValue;
   StepParams sp{};
   if (fused_step) sp = *fused_step;

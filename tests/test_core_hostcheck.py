@@ -136,3 +136,39 @@ def test_bitboard_rule_equals_general_rule_on_random_small_puzzles():
                 assert np.array_equal(got, want), text
             checked += 1
     assert checked > 100
+
+
+def test_general_rule_matches_oracle_on_irregular_puzzles():
+    """Random puzzles with overlapping objects ('+' cells), movables inside walls and agents on
+    agent walls: the kernels' general rule against the Python oracle, state by state (objects
+    may leave the grid here)."""
+    import pushworld_oracle as po
+
+    rng = np.random.default_rng(77)
+    names_pool = ["a", "m0", "m1", "m2", "m3", "w", "aw", "g0", "g1"]
+    checked = 0
+    for trial in range(120):
+        w, h = int(rng.integers(2, 8)), int(rng.integers(2, 7))
+        grid = [[[] for _ in range(w)] for _ in range(h)]
+        for name in names_pool:
+            for _ in range(int(rng.integers(0, 4)) + (1 if name == "a" else 0)):
+                x, y = int(rng.integers(w)), int(rng.integers(h))
+                if name not in grid[y][x]:
+                    grid[y][x].append(name)
+        text = "\n".join(" ".join("+".join(c) if c else "." for c in row) for row in grid) + "\n"
+        try:
+            oracle = po.OraclePuzzle(text)
+        except (ValueError, AssertionError):
+            continue
+        blob = tables.compile_text(text)
+        actions = rng.integers(0, 4, size=120).astype(np.uint8)
+        states, moved, ach = hostcheck.walk(blob, oracle.initial_state, actions)
+        state = oracle.initial_state
+        for t, a in enumerate(actions):
+            state, moved_idx = oracle.get_next_state_and_moved(state, int(a))
+            got = tuple((int(x), int(y)) for x, y in states[t])
+            assert got == state, (text, t)
+            assert int(moved[t]) == sum(1 << k for k in moved_idx), (text, t)
+            assert int(ach[t]) == oracle.count_achieved_goals(state)
+        checked += 1
+    assert checked > 60
