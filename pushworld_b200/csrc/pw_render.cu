@@ -40,6 +40,7 @@ cudaError_t upload_palette(const uint8_t* rgb, const float* rgb_f32, int n_color
 namespace {
 
 constexpr int kRenderBlock = 256;
+constexpr size_t kRenderMaxDynamicSmem = 227 * 1024 - 2048;
 
 struct SmemPos {
   const int* sx;
@@ -217,7 +218,7 @@ cudaError_t launch_render(const RenderParams& p, const StepParams* fused_step, i
   const size_t row_pitch = ((size_t)p.out_w * 3 * elem + 15) & ~(size_t)15;
   const size_t smem = (size_t)p.max_blob_u64 * 8 + (size_t)p.max_cells * 8 + 64 * sizeof(int) +
                       (size_t)p.out_w * 2 + 16 + 7 * row_pitch;
-  if (smem > 227 * 1024) return cudaErrorInvalidValue;
+  if (smem > kRenderMaxDynamicSmem) return cudaErrorInvalidValue;
   StepParams sp{};
   if (fused_step) sp = *fused_step;
 #define PW_LAUNCH(T, F) k_render<T, F><<<(unsigned)p.N, kRenderBlock, smem, stream>>>(p, sp)
@@ -233,8 +234,9 @@ cudaError_t launch_render(const RenderParams& p, const StepParams* fused_step, i
 }
 
 cudaError_t configure_render_kernels() {
-  // opt in to the full 227 KB of dynamic shared memory once per device
-  const int cap = 227 * 1024;
+  // opt in to (almost) the full 227 KB of shared memory once per device; the kernels also use a
+  // little static shared memory, which counts against the same limit
+  const int cap = (int)kRenderMaxDynamicSmem;
   cudaError_t err = cudaFuncSetAttribute(k_render<float, false>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
   if (err == cudaSuccess)
