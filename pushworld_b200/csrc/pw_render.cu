@@ -95,15 +95,19 @@ __device__ __forceinline__ void put_pixel<uint8_t>(uint8_t* dst, uint32_t pal, c
   dst[2] = (uint8_t)((c >> 16) & 0xffu);
 }
 
+// Persistent CTAs: CTA b owns the contiguous environments [b*chunk, (b+1)*chunk).  Fused mode
+// first steps all of them (one thread per environment, coalesced state access), then the block
+// renders them one after the other; the puzzle table, the pixel-column map and the palette are
+// staged once per CTA and only re-staged when the puzzle changes.
 template <typename T, bool kFused>
 __global__ void __launch_bounds__(kRenderBlock) k_render(const RenderParams p, const StepParams sp) {
   extern __shared__ __align__(16) uint64_t smem[];
   __shared__ float4 s_pal_f[16];
   __shared__ uint32_t s_pal_u[16];
-  const int64_t e = blockIdx.x;
-  const int pid = p.puzzle_id ? p.puzzle_id[e] : p.puzzle_uniform;
-  const uint64_t* g_tbl = p.blob + p.puzzle_off[pid];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+  const int64_t chunk = (p.N + gridDim.x - 1) / gridDim.x;
+  const int64_t e0 = (int64_t)blockIdx.x * chunk;
+  const int64_t e1 = (e0 + chunk) < p.N ? (e0 + chunk) : p.N;
 
   // ---- shared memory carve-up -----------------------------------------------------------
   uint64_t* s_tbl = smem;                                   // max_blob_u64
@@ -118,93 +122,107 @@ __global__ void __launch_bounds__(kRenderBlock) k_render(const RenderParams p, c
       (reinterpret_cast<uintptr_t>(s_xmap + p.out_w) + 15) & ~static_cast<uintptr_t>(15));
   uint8_t* s_zero = s_pat + 6 * row_pitch;
 
-  const int n_u64 = (int)__ldg(reinterpret_cast<const uint32_t*>(g_tbl) + kHdrSizeU64);
-  for (int i = threadIdx.x; i < n_u64; i += blockDim.x) s_tbl[i] = __ldg(g_tbl + i);
   if (threadIdx.x < 16) {
     s_pal_f[threadIdx.x] = make_float4(c_pal_f32[threadIdx.x][0], c_pal_f32[threadIdx.x][1],
                                        c_pal_f32[threadIdx.x][2], 0.f);
     s_pal_u[threadIdx.x] = (uint32_t)c_pal_u8[threadIdx.x][0] | ((uint32_t)c_pal_u8[threadIdx.x][1] << 8) |
                            ((uint32_t)c_pal_u8[threadIdx.x][2] << 16);
   }
-  __syncthreads();
-  const SharedTable tbl{s_tbl};
-  const uint32_t dims = tbl.word(kHdrDims);
-  const int W = (int)(dims & 0xffffu), H = (int)(dims >> 16);
-  const int n = (int)(tbl.word(kHdrCounts) & 0xffffu);
-  const int ppc = p.ppc, bw = p.bw;
-  const int img_h = H * ppc, img_w = W * ppc;
-  const int pad_top = (p.out_h - img_h) / 2, pad_left = (p.out_w - img_w) / 2;  // env_utils.py:81-82
+  for (int i = threadIdx.x; i < (row_pitch >> 2); i += blockDim.x)
+    reinterpret_cast<uint32_t*>(s_zero)[i] = 0u;
 
-  // ---- state (and the fused step) -----------------------------------------------------
+  // ---- fused step of this CTA's environments (BASELINE config 5) ------------------------
   if (kFused) {
-    if (threadIdx.x == 0) {
-      SmemEnv<SharedTable> env;
-      env.init(tbl, s_x, s_y, 1);
+    uint32_t invalid = 0;
+    for (int64_t e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
+      const int pid = sp.puzzle_id ? sp.puzzle_id[e] : sp.puzzle_uniform;
+      LocalEnv<GlobalTable> env;
+      env.init(GlobalTable{sp.blob + sp.puzzle_off[pid]});
       StepCounts counts;
       run_steps_thread<false>(env, sp, e, counts);
-      if (counts.invalid && sp.status) atomicAdd(&sp.status[0], (unsigned long long)counts.invalid);
+      invalid += counts.invalid;
     }
-  } else {
+    if (invalid && sp.status) atomicAdd(&sp.status[0], (unsigned long long)invalid);
+  }
+  __syncthreads();  // new states (global memory) visible to the whole block
+
+  const int ppc = p.ppc, bw = p.bw;
+  int cur_pid = -1, W = 0, H = 0, n = 0, img_h = 0, img_w = 0, pad_top = 0, pad_left = 0;
+  for (int64_t e = e0; e < e1; ++e) {
+    const int pid = p.puzzle_id ? p.puzzle_id[e] : p.puzzle_uniform;
+    if (pid != cur_pid) {  // block-uniform branch
+      cur_pid = pid;
+      const uint64_t* g_tbl = p.blob + p.puzzle_off[pid];
+      const int n_u64 = (int)__ldg(reinterpret_cast<const uint32_t*>(g_tbl) + kHdrSizeU64);
+      for (int i = threadIdx.x; i < n_u64; i += blockDim.x) s_tbl[i] = __ldg(g_tbl + i);
+      const uint32_t dims = __ldg(reinterpret_cast<const uint32_t*>(g_tbl) + kHdrDims);
+      W = (int)(dims & 0xffffu);
+      H = (int)(dims >> 16);
+      n = (int)(__ldg(reinterpret_cast<const uint32_t*>(g_tbl) + kHdrCounts) & 0xffffu);
+      img_h = H * ppc;
+      img_w = W * ppc;
+      pad_top = (p.out_h - img_h) / 2;   // env_utils.py:81-82
+      pad_left = (p.out_w - img_w) / 2;
+      // pixel column -> (cell column, region) map, shared by every cell row of the frame
+      for (int X = threadIdx.x; X < p.out_w; X += blockDim.x) {
+        const int xi = X - pad_left;
+        uint16_t m = 0xffffu;  // zero padding
+        if (xi >= 0 && xi < img_w) {
+          const int cx = xi / ppc;
+          m = (uint16_t)((cx << 2) | region_of(xi - cx * ppc, ppc, bw));
+        }
+        s_xmap[X] = m;
+      }
+    }
     for (int j = threadIdx.x; j < n; j += blockDim.x) {
       s_x[j] = p.x[j * p.stride + e];
       s_y[j] = p.y[j * p.stride + e];
     }
-  }
-  // pixel column -> (cell column, region) map, shared by every cell row of the frame
-  for (int X = threadIdx.x; X < p.out_w; X += blockDim.x) {
-    const int xi = X - pad_left;
-    uint16_t m = 0xffffu;  // zero padding
-    if (xi >= 0 && xi < img_w) {
-      const int cx = xi / ppc;
-      m = (uint16_t)((cx << 2) | region_of(xi - cx * ppc, ppc, bw));
-    }
-    s_xmap[X] = m;
-  }
-  for (int i = threadIdx.x; i < (row_pitch >> 2); i += blockDim.x)
-    reinterpret_cast<uint32_t*>(s_zero)[i] = 0u;
-  __syncthreads();
-
-  // ---- 1. cell codes --------------------------------------------------------------------
-  const SmemPos pos{s_x, s_y};
-  for (int c = threadIdx.x; c < W * H; c += blockDim.x) {
-    const int cy = c / W, cx = c - cy * W;
-    s_code[c] = cell_code(tbl, pos, cx, cy);
-  }
-
-  // ---- 2. pixel rows --------------------------------------------------------------------
-  uint8_t* frame = static_cast<uint8_t*>(p.out) + (size_t)e * (size_t)p.out_h * (size_t)row_bytes;
-  const bool vec16 = (row_bytes & 15) == 0 && (reinterpret_cast<uintptr_t>(frame) & 15) == 0;
-  const bool vec4 = (row_bytes & 3) == 0 && (reinterpret_cast<uintptr_t>(frame) & 3) == 0;
-  auto emit = [&](int Y, const uint8_t* src) {  // one warp writes one output row
-    uint8_t* dst = frame + (size_t)Y * (size_t)row_bytes;
-    if (vec16) copy_row<16>(dst, src, row_bytes, lane);
-    else if (vec4) copy_row<4>(dst, src, row_bytes, lane);
-    else copy_row<1>(dst, src, row_bytes, lane);
-  };
-  // builds the 3 region-row patterns of cell row cy into pattern set `buf`
-  auto build = [&](int cy, int buf) {
-    uint8_t* set = s_pat + buf * 3 * row_pitch;
-    for (int i = threadIdx.x; i < 3 * p.out_w; i += blockDim.x) {
-      const int rr = i / p.out_w, X = i - rr * p.out_w;
-      const uint32_t m = s_xmap[X];
-      uint32_t pal = kPalPad;
-      if (m != 0xffffu) pal = (uint32_t)(s_code[cy * W + (m >> 2)] >> (4 * (rr * 3 + (m & 3u)))) & 15u;
-      put_pixel<T>(reinterpret_cast<T*>(set + rr * row_pitch) + 3 * X, pal, s_pal_f, s_pal_u);
-    }
-  };
-
-  __syncthreads();  // codes + zero row ready
-  for (int Y = warp; Y < pad_top; Y += n_warps) emit(Y, s_zero);
-  for (int Y = pad_top + img_h + warp; Y < p.out_h; Y += n_warps) emit(Y, s_zero);
-  build(0, 0);
-  __syncthreads();
-  for (int cy = 0; cy < H; ++cy) {
-    if (cy + 1 < H) build(cy + 1, (cy + 1) & 1);  // next cell row while this one streams out
-    const uint8_t* set = s_pat + (cy & 1) * 3 * row_pitch;
-    const int Y0 = pad_top + cy * ppc;
-    for (int oy = warp; oy < ppc; oy += n_warps)
-      emit(Y0 + oy, set + region_of(oy, ppc, bw) * row_pitch);
     __syncthreads();
+    const SharedTable tbl{s_tbl};
+
+    // ---- 1. cell codes ------------------------------------------------------------------
+    const SmemPos pos{s_x, s_y};
+    for (int c = threadIdx.x; c < W * H; c += blockDim.x) {
+      const int cy = c / W, cx = c - cy * W;
+      s_code[c] = cell_code(tbl, pos, cx, cy);
+    }
+
+    // ---- 2. pixel rows ------------------------------------------------------------------
+    uint8_t* frame = static_cast<uint8_t*>(p.out) + (size_t)e * (size_t)p.out_h * (size_t)row_bytes;
+    const bool vec16 = (row_bytes & 15) == 0 && (reinterpret_cast<uintptr_t>(frame) & 15) == 0;
+    const bool vec4 = (row_bytes & 3) == 0 && (reinterpret_cast<uintptr_t>(frame) & 3) == 0;
+    auto emit = [&](int Y, const uint8_t* src) {  // one warp writes one output row
+      uint8_t* dst = frame + (size_t)Y * (size_t)row_bytes;
+      if (vec16) copy_row<16>(dst, src, row_bytes, lane);
+      else if (vec4) copy_row<4>(dst, src, row_bytes, lane);
+      else copy_row<1>(dst, src, row_bytes, lane);
+    };
+    // builds the 3 region-row patterns of cell row cy into pattern set `buf`
+    auto build = [&](int cy, int buf) {
+      uint8_t* set = s_pat + buf * 3 * row_pitch;
+      for (int i = threadIdx.x; i < 3 * p.out_w; i += blockDim.x) {
+        const int rr = i / p.out_w, X = i - rr * p.out_w;
+        const uint32_t m = s_xmap[X];
+        uint32_t pal = kPalPad;
+        if (m != 0xffffu) pal = (uint32_t)(s_code[cy * W + (m >> 2)] >> (4 * (rr * 3 + (m & 3u)))) & 15u;
+        put_pixel<T>(reinterpret_cast<T*>(set + rr * row_pitch) + 3 * X, pal, s_pal_f, s_pal_u);
+      }
+    };
+
+    for (int Y = warp; Y < pad_top; Y += n_warps) emit(Y, s_zero);
+    for (int Y = pad_top + img_h + warp; Y < p.out_h; Y += n_warps) emit(Y, s_zero);
+    __syncthreads();  // codes ready
+    build(0, 0);
+    __syncthreads();
+    for (int cy = 0; cy < H; ++cy) {
+      if (cy + 1 < H) build(cy + 1, (cy + 1) & 1);  // next cell row while this one streams out
+      const uint8_t* set = s_pat + (cy & 1) * 3 * row_pitch;
+      const int Y0 = pad_top + cy * ppc;
+      for (int oy = warp; oy < ppc; oy += n_warps)
+        emit(Y0 + oy, set + region_of(oy, ppc, bw) * row_pitch);
+      __syncthreads();
+    }
   }
 }
 
@@ -221,7 +239,16 @@ cudaError_t launch_render(const RenderParams& p, const StepParams* fused_step, i
   if (smem > kRenderMaxDynamicSmem) return cudaErrorInvalidValue;
   StepParams sp{};
   if (fused_step) sp = *fused_step;
-#define PW_LAUNCH(T, F) k_render<T, F><<<(unsigned)p.N, kRenderBlock, smem, stream>>>(p, sp)
+  // persistent grid: enough CTAs to fill the machine several times over, never more than N
+  int sm_count = 148;
+  {
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess)
+      cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const int64_t want = (int64_t)sm_count * 16;
+  const unsigned grid = (unsigned)(p.N < want ? p.N : want);
+#define PW_LAUNCH(T, F) k_render<T, F><<<grid, kRenderBlock, smem, stream>>>(p, sp)
   if (p.dtype == 1) {
     if (fused_step) PW_LAUNCH(float, true);
     else PW_LAUNCH(float, false);
