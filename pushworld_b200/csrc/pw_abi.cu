@@ -60,6 +60,8 @@ struct PwEngine {
   uint64_t* d_blob = nullptr;
   uint32_t* d_off = nullptr;
   unsigned long long* d_status = nullptr;  // [4]
+  pw::BoardStaticPod* d_board_static = nullptr;  // [num_puzzles]
+  std::vector<int> board_bits;                    // per puzzle, 1 << 30 = not eligible
 };
 
 using namespace pw;
@@ -81,11 +83,57 @@ int check_common(const PwEngine* e, int64_t n, const int32_t* puzzle_id, int puz
 #define PW_RETURN_IF_EMPTY(n) \
   if ((n) == 0) return PW_OK
 
-// bitboard kernels (pw_board.cuh): the interior fits one machine word and the puzzle starts in a
-// regular state; returns the number of bits needed, 1 << 30 if not eligible
-int board_bits_of(const PuzzleInfo& info) {
-  if (!(info.flags & PW_TABLE_FLAG_REGULAR)) return 1 << 30;
-  return board_bits(info.width, info.height);
+// Host view of a table blob for the host-side use of pw_board.cuh.
+struct HostTable {
+  const uint64_t* base;
+  PW_HD uint64_t row(int off) const { return base[off]; }
+  PW_HD uint32_t word(int i) const { return reinterpret_cast<const uint32_t*>(base)[i]; }
+};
+
+// initial x / y of object k, read from the descriptors
+struct InitCoord {
+  HostTable t;
+  int desc_word;
+  bool want_y;
+  PW_HD int operator()(int k) const {
+    const uint32_t v = t.word(desc_word + 4 * k + 1);
+    return want_y ? hi16(v) : lo16(v);
+  }
+};
+
+// bitboard kernels (pw_board.cuh): the interior fits one machine word, n <= 8 and the puzzle
+// starts in a regular state.  Fills `pod` (bits = 1 << 30 when not eligible).
+void make_board_static(const PuzzleInfo& info, const uint64_t* blob, BoardStaticPod* pod) {
+  memset(pod, 0, sizeof(*pod));
+  pod->bits = 1 << 30;
+  if (!(info.flags & PW_TABLE_FLAG_REGULAR) || info.n > 8) return;
+  const int bits = board_bits(info.width, info.height);
+  if (bits > 64) return;
+  HostTable t{blob};
+  Board<8, uint64_t> s;
+  board_init(s, t);
+  const int desc_word = (int)t.word(kHdrObjOff) * 2;
+  const bool ok = board_load(s, t, InitCoord{t, desc_word, false}, InitCoord{t, desc_word, true});
+  if (!ok) return;
+  BoardAction<uint64_t> act[4];
+  board_action_table(s, act);
+  pod->wall = s.wall;
+  pod->awall = s.awall;
+  pod->edge_up = s.edge_up;
+  pod->edge_down = s.edge_down;
+  for (int k = 0; k < 8; ++k) {
+    pod->goal[k] = s.goal[k];
+    pod->init[k] = s.b[k];
+  }
+  for (int a = 0; a < 4; ++a) {
+    pod->act_edge[a] = act[a].edge;
+    pod->act_sl[a] = act[a].sl;
+    pod->act_sr[a] = act[a].sr;
+  }
+  pod->P = s.P;
+  pod->n = s.n;
+  pod->g = s.g;
+  pod->bits = bits;
 }
 
 int n_limit_of(const PwEngine* e, const int32_t* puzzle_id, int puzzle_uniform) {
@@ -170,9 +218,20 @@ int pw_engine_create(const void* blob, size_t blob_bytes, const uint32_t* offset
     e->max_blob_u64 = info.size_u64 > e->max_blob_u64 ? info.size_u64 : e->max_blob_u64;
   }
 
+  std::vector<BoardStaticPod> pods((size_t)num_puzzles);
+  for (int p = 0; p < num_puzzles; ++p) {
+    make_board_static(e->puzzles[(size_t)p],
+                      reinterpret_cast<const uint64_t*>(bytes) + offsets_u64[p], &pods[(size_t)p]);
+    e->board_bits.push_back(pods[(size_t)p].bits);
+  }
+
   DeviceGuard guard(device);
   cudaError_t err = cudaSetDevice(device);
   if (err == cudaSuccess) err = cudaMalloc(&e->d_blob, blob_bytes);
+  if (err == cudaSuccess) err = cudaMalloc(&e->d_board_static, sizeof(BoardStaticPod) * pods.size());
+  if (err == cudaSuccess)
+    err = cudaMemcpy(e->d_board_static, pods.data(), sizeof(BoardStaticPod) * pods.size(),
+                     cudaMemcpyHostToDevice);
   if (err == cudaSuccess) err = cudaMalloc(&e->d_off, sizeof(uint32_t) * (size_t)num_puzzles);
   if (err == cudaSuccess) err = cudaMalloc(&e->d_status, sizeof(unsigned long long) * 4);
   if (err == cudaSuccess) err = cudaMemcpy(e->d_blob, blob, blob_bytes, cudaMemcpyHostToDevice);
@@ -220,6 +279,7 @@ int pw_engine_destroy(PwEngine* e) {
   if (e->d_blob) cudaFree(e->d_blob);
   if (e->d_off) cudaFree(e->d_off);
   if (e->d_status) cudaFree(e->d_status);
+  if (e->d_board_static) cudaFree(e->d_board_static);
   delete e;
   return PW_OK;
 }
@@ -295,7 +355,8 @@ int pw_rollout(PwEngine* e, int64_t n_envs, int32_t n_steps, const int32_t* puzz
   p.puzzle_uniform = puzzle_id ? 0 : puzzle_uniform;
   p.uniform_u64 = puzzle_id ? 0 : e->puzzles[(size_t)puzzle_uniform].size_u64;
   p.n_max = e->n_max;
-  p.board_bits = puzzle_id ? (1 << 30) : board_bits_of(e->puzzles[(size_t)puzzle_uniform]);
+  p.board_bits = puzzle_id ? (1 << 30) : e->board_bits[(size_t)puzzle_uniform];
+  p.board_static = puzzle_id ? nullptr : e->d_board_static + puzzle_uniform;
   p.x = x;
   p.y = y;
   p.stride = stride;
@@ -336,7 +397,8 @@ int pw_step(PwEngine* e, int64_t n_envs, const int32_t* puzzle_id, int puzzle_un
   p.puzzle_uniform = puzzle_id ? 0 : puzzle_uniform;
   p.uniform_u64 = puzzle_id ? 0 : e->puzzles[(size_t)puzzle_uniform].size_u64;
   p.n_max = e->n_max;
-  p.board_bits = puzzle_id ? (1 << 30) : board_bits_of(e->puzzles[(size_t)puzzle_uniform]);
+  p.board_bits = puzzle_id ? (1 << 30) : e->board_bits[(size_t)puzzle_uniform];
+  p.board_static = puzzle_id ? nullptr : e->d_board_static + puzzle_uniform;
   p.x = x;
   p.y = y;
   p.stride = stride;
@@ -485,7 +547,8 @@ int pw_step_render(PwEngine* e, int64_t n_envs, const int32_t* puzzle_id, int pu
   p.puzzle_uniform = puzzle_id ? 0 : puzzle_uniform;
   p.uniform_u64 = puzzle_id ? 0 : e->puzzles[(size_t)puzzle_uniform].size_u64;
   p.n_max = e->n_max;
-  p.board_bits = puzzle_id ? (1 << 30) : board_bits_of(e->puzzles[(size_t)puzzle_uniform]);
+  p.board_bits = puzzle_id ? (1 << 30) : e->board_bits[(size_t)puzzle_uniform];
+  p.board_static = puzzle_id ? nullptr : e->d_board_static + puzzle_uniform;
   p.x = x;
   p.y = y;
   p.stride = stride;

@@ -7,6 +7,16 @@ namespace pw {
 
 constexpr uint32_t kFlagAutoreset = 1u;
 
+// Host-precomputed static boards of a bitboard-eligible puzzle (pw_board.cuh), one per puzzle.
+struct BoardStaticPod {
+  uint64_t wall, awall, edge_up, edge_down;
+  uint64_t goal[8];
+  uint64_t init[8];
+  uint64_t act_edge[4];
+  uint32_t act_sl[4], act_sr[4];
+  int32_t P, n, g, bits;  // bits = 1 << 30 when the puzzle is not eligible
+};
+
 struct StepParams {
   const uint64_t* blob;        // all puzzle tables, device
   const uint32_t* puzzle_off;  // u64 offset of each puzzle inside blob, device
@@ -17,6 +27,7 @@ struct StepParams {
   int32_t uniform_u64;  // blob size of puzzle_uniform (u64 units)
   int32_t n_max;        // planes in x / y
   int32_t board_bits;   // bits puzzle_uniform needs in board form if it is regular, else 1 << 30
+  const BoardStaticPod* board_static;  // device; entry of puzzle_uniform (valid if board_bits <= 64)
   int32_t* x;
   int32_t* y;
   int64_t stride;

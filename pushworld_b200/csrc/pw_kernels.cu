@@ -149,28 +149,28 @@ __global__ void __launch_bounds__(kBlock, MIN_BLOCKS)
   __shared__ uint32_t s_counters[4];
   __shared__ BoardStatic<Word> st;
   if (threadIdx.x < 4) s_counters[threadIdx.x] = 0;
-  stage_table(smem, p.blob + p.puzzle_off[p.puzzle_uniform], p.uniform_u64);
   const SharedTable tbl{smem};
-  if (threadIdx.x == 0) {
-    Board<NMAX, Word> tmp;
-    board_init(tmp, tbl);
-    const int desc_word = (int)tbl.word(kHdrObjOff) * 2;
-    board_load(tmp, tbl, [&](int k) { return lo16(tbl.word(desc_word + 4 * k + 1)); },
-               [&](int k) { return hi16(tbl.word(desc_word + 4 * k + 1)); });
-    st.wall = tmp.wall;
-    st.awall = tmp.awall;
-    st.edge_up = tmp.edge_up;
-    st.edge_down = tmp.edge_down;
-    st.P = tmp.P;
-    st.n = tmp.n;
-    st.g = tmp.g;
-    board_action_table(tmp, st.act);
-    for (int k = 0; k < NMAX; ++k) {
-      st.goal[k] = tmp.goal[k];
-      st.init[k] = tmp.b[k];
-    }
+  // static boards were computed on the host at engine creation (pw_abi.cu: make_board_static)
+  const BoardStaticPod* __restrict__ pod = p.board_static;
+  if (threadIdx.x < 8) {
+    st.goal[threadIdx.x] = (Word)__ldg(&pod->goal[threadIdx.x]);
+    st.init[threadIdx.x] = (Word)__ldg(&pod->init[threadIdx.x]);
   }
-  __syncthreads();
+  if (threadIdx.x < 4) {
+    st.act[threadIdx.x].edge = (Word)__ldg(&pod->act_edge[threadIdx.x]);
+    st.act[threadIdx.x].sl = __ldg(&pod->act_sl[threadIdx.x]);
+    st.act[threadIdx.x].sr = __ldg(&pod->act_sr[threadIdx.x]);
+  }
+  if (threadIdx.x == 0) {
+    st.wall = (Word)__ldg(&pod->wall);
+    st.awall = (Word)__ldg(&pod->awall);
+    st.edge_up = (Word)__ldg(&pod->edge_up);
+    st.edge_down = (Word)__ldg(&pod->edge_down);
+    st.P = __ldg(&pod->P);
+    st.n = __ldg(&pod->n);
+    st.g = __ldg(&pod->g);
+  }
+  stage_table(smem, p.blob + p.puzzle_off[p.puzzle_uniform], p.uniform_u64);  // ends with a barrier
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   StepCounts c;
   if (e < p.N) {

@@ -246,7 +246,10 @@ cudaError_t launch_render(const RenderParams& p, const StepParams* fused_step, i
     if (cudaGetDevice(&dev) == cudaSuccess)
       cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
   }
-  const int64_t want = (int64_t)sm_count * 16;
+  // at most ~4 frames per CTA: amortises the per-CTA staging without turning the output into
+  // thousands of far-apart write streams
+  int64_t want = (int64_t)sm_count * 16;
+  if ((p.N + 3) / 4 > want) want = (p.N + 3) / 4;
   const unsigned grid = (unsigned)(p.N < want ? p.N : want);
 #define PW_LAUNCH(T, F) k_render<T, F><<<grid, kRenderBlock, smem, stream>>>(p, sp)
   if (p.dtype == 1) {
