@@ -136,7 +136,8 @@ def cpu_port_throughput(target_seconds: float, threads: int = 0):
     from pushworld_b200 import data
 
     puzzle = c_oracle.COraclePuzzle(data.puzzle_text(PUZZLE_KEY))
-    threads = threads or c_oracle.max_threads()
+    # all host threads this process may use (torchrun exports OMP_NUM_THREADS=1: ignore it)
+    threads = threads or len(os.sched_getaffinity(0))
     rng = np.random.default_rng(ACTION_SEED)
 
     def run(n_envs, n_steps):
