@@ -51,45 +51,54 @@ __device__ __forceinline__ void run_steps_sim(Sim& sim, const StepParams& p, int
   float* __restrict__ reward = p.reward;
   uint8_t* __restrict__ terminated = p.terminated;
   const float r_plain = c_reward_lut[kMaxObjects];  // -0.01f
-  int a_next = kLean ? actions[off] : actions[e];
-  for (int t = 0; t < T; ++t) {
-    const int a = a_next;
-    if (kLean) {
-      if (t + 1 < T) a_next = actions[off + n32];  // prefetch: independent of the state
-    } else {
-      if (t + 1 < T) a_next = actions[(int64_t)(t + 1) * N + e];
-    }
-    const uint32_t moved = sim.do_step(a);
-    const int ach = Sim::kCheapAchieved ? sim.achieved() : (moved ? sim.achieved() : prev);
-    const bool term = ach == g;  // puzzle.py:409-411
-    const int dg = ach - prev;
-    prev = ach;
-    // gym_env.py:212-221; the float64 value (dg - 0.01) was rounded to float32 once, on the host
-    float r = r_plain;
-    if (dg != 0) r = c_reward_lut[dg + kMaxObjects];
-    r = term ? 10.0f : r;
-    if (term) ++c.terminated;
-    if (moved) ++c.moved;
-    c.dgoals += (uint32_t)max(dg, 0);
-    if ((unsigned)a > 3u) ++c.invalid;
-    if (kLean) {
-      reward[off] = r;
-      terminated[off] = term ? 1 : 0;
-      off += n32;
-    } else {
-      const int64_t idx = (int64_t)t * N + e;
-      ++steps;
-      const bool trunc = p.max_steps > 0 && steps >= p.max_steps;  // gym_env.py:223
-      if (p.reward) p.reward[idx] = r;
-      if (p.dgoals) p.dgoals[idx] = (int8_t)dg;
-      if (p.terminated) p.terminated[idx] = term ? 1 : 0;
-      if (p.truncated) p.truncated[idx] = trunc ? 1 : 0;
-      if (p.moved) p.moved[idx] = moved;
-      ret += r;
-      if ((p.flags & kFlagAutoreset) && (term || trunc)) {
-        sim.load_initial();
-        prev = sim.achieved();
-        steps = 0;
+  // Actions are independent of the state, so they are fetched kPrefetch steps ahead: with ~8
+  // warps per scheduler a single step of look-ahead does not cover the DRAM latency.
+  constexpr int kPrefetch = 4;
+  int ring[kPrefetch];
+#pragma unroll
+  for (int k = 0; k < kPrefetch; ++k)
+    ring[k] = k < T ? (kLean ? actions[off + (uint32_t)k * n32] : actions[(int64_t)k * N + e]) : 0;
+  for (int t0 = 0; t0 < T; t0 += kPrefetch) {
+#pragma unroll
+    for (int k = 0; k < kPrefetch; ++k) {
+      const int t = t0 + k;
+      if (t >= T) break;
+      const int a = ring[k];
+      if (t + kPrefetch < T)
+        ring[k] = kLean ? actions[off + (uint32_t)kPrefetch * n32]
+                        : actions[(int64_t)(t + kPrefetch) * N + e];
+      const uint32_t moved = sim.do_step(a);
+      const int ach = Sim::kCheapAchieved ? sim.achieved() : (moved ? sim.achieved() : prev);
+      const bool term = ach == g;  // puzzle.py:409-411
+      const int dg = ach - prev;
+      prev = ach;
+      // gym_env.py:212-221; the float64 value (dg - 0.01) was rounded to float32 once, on the host
+      float r = r_plain;
+      if (dg != 0) r = c_reward_lut[dg + kMaxObjects];
+      r = term ? 10.0f : r;
+      if (term) ++c.terminated;
+      if (moved) ++c.moved;
+      c.dgoals += (uint32_t)max(dg, 0);
+      if ((unsigned)a > 3u) ++c.invalid;
+      if (kLean) {
+        reward[off] = r;
+        terminated[off] = term ? 1 : 0;
+        off += n32;
+      } else {
+        const int64_t idx = (int64_t)t * N + e;
+        ++steps;
+        const bool trunc = p.max_steps > 0 && steps >= p.max_steps;  // gym_env.py:223
+        if (p.reward) p.reward[idx] = r;
+        if (p.dgoals) p.dgoals[idx] = (int8_t)dg;
+        if (p.terminated) p.terminated[idx] = term ? 1 : 0;
+        if (p.truncated) p.truncated[idx] = trunc ? 1 : 0;
+        if (p.moved) p.moved[idx] = moved;
+        ret += r;
+        if ((p.flags & kFlagAutoreset) && (term || trunc)) {
+          sim.load_initial();
+          prev = sim.achieved();
+          steps = 0;
+        }
       }
     }
   }
