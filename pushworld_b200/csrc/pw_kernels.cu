@@ -114,6 +114,7 @@ struct BoardStatic {
 template <int NMAX, typename Word>
 struct BoardSim {
   static constexpr bool kCheapAchieved = true;
+  static constexpr int kPrefetch = 4;
   Board<NMAX, Word>& s;
   const BoardStatic<Word>& st;
   __device__ __forceinline__ void store(const StepParams& p, int64_t e) {

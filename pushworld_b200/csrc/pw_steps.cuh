@@ -29,6 +29,7 @@ struct GeneralSim {
   __device__ __forceinline__ int achieved() const { return achieved_goals(env); }
   __device__ __forceinline__ int goals() const { return env.g(); }
   static constexpr bool kCheapAchieved = false;
+  static constexpr int kPrefetch = 1;
 };
 
 // `Sim` provides load / store / load_initial / do_step / achieved / goals.
@@ -53,7 +54,7 @@ __device__ __forceinline__ void run_steps_sim(Sim& sim, const StepParams& p, int
   const float r_plain = c_reward_lut[kMaxObjects];  // -0.01f
   // Actions are independent of the state, so they are fetched kPrefetch steps ahead: with ~8
   // warps per scheduler a single step of look-ahead does not cover the DRAM latency.
-  constexpr int kPrefetch = 4;
+  constexpr int kPrefetch = Sim::kPrefetch;  // 1 for the (large) general rule: unrolling it thrashes the I-cache
   int ring[kPrefetch];
 #pragma unroll
   for (int k = 0; k < kPrefetch; ++k)
