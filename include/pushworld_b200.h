@@ -183,6 +183,28 @@ PW_API int pw_expand(PwEngine* engine, int64_t n_states, const int32_t* puzzle_i
               const int32_t* x_in, const int32_t* y_in, int64_t stride_in, int32_t* x_out,
               int32_t* y_out, int64_t stride_out, uint32_t* moved, uint8_t* goal, void* stream);
 
+/* pw_expand reading its inputs through an index list: state e is column index[e] of x_in / y_in
+ * (a frontier scattered over a larger state arena).  index: device int64[n_states]. */
+PW_API int pw_expand_indexed(PwEngine* engine, int64_t n_states, int puzzle, const int64_t* index,
+                      const int32_t* x_in, const int32_t* y_in, int64_t stride_in, int32_t* x_out,
+                      int32_t* y_out, int64_t stride_out, uint32_t* moved, uint8_t* goal,
+                      void* stream);
+
+/* Exact visited-set insertion for expanded frontiers (the `visited.find / insert` of
+ * cpp/include/search/best_first_search.h:81-91 with StateHash, cpp/include/pushworld_puzzle.h:74-78,
+ * batched).  All states of a search live in ONE caller-owned arena (SoA planes x / y, `stride`
+ * columns); a state's id is its column.  `table` is a caller-owned open-addressing hash set:
+ * uint64[capacity], capacity a power of two, zero-initialised = empty; an entry packs a 24-bit
+ * fingerprint and the id of the first state inserted with that content.  For the `count` states
+ * with ids first_id .. first_id+count-1 (only those with valid[i] != 0 if `valid` is non-NULL):
+ *   is_new[i] = 1 if no equal state was in the set (the state is then inserted), else 0.
+ * Equality is checked on the full positions, never on the hash alone, so the result is exact;
+ * among equal states of one call exactly one is reported new.  If the table fills up the
+ * engine's status word 1 (pw_engine_poll) is incremented and the state is reported not new. */
+PW_API int pw_visited_insert(PwEngine* engine, int puzzle, const int32_t* x, const int32_t* y,
+                      int64_t stride, int64_t first_id, int64_t count, const uint8_t* valid,
+                      uint64_t* table, int64_t capacity, uint8_t* is_new, void* stream);
+
 /* RGB image of every environment's state.
  * Replaces: PushWorldPuzzle.render + _draw_object (puzzle.py:426-469,596-638) and, with
  * dtype F32 and padding, render_observation_padded (env_utils.py:44-91).

@@ -57,6 +57,16 @@ SIGNATURES = {
         [c_void_p, c_int64, c_void_p, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
          c_int64, c_void_p, c_void_p, c_void_p],
     ),
+    "pw_expand_indexed": (
+        c_int,
+        [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
+         c_int64, c_void_p, c_void_p, c_void_p],
+    ),
+    "pw_visited_insert": (
+        c_int,
+        [c_void_p, c_int, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p,
+         c_int64, c_void_p, c_void_p],
+    ),
     "pw_render": (
         c_int,
         [c_void_p, c_int64, c_void_p, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int,

@@ -475,6 +475,71 @@ int pw_expand(PwEngine* e, int64_t n_states, const int32_t* puzzle_id, int puzzl
   return err == cudaSuccess ? PW_OK : cuda_error(err, "pw_expand");
 }
 
+int pw_expand_indexed(PwEngine* e, int64_t n_states, int puzzle, const int64_t* index,
+                      const int32_t* x_in, const int32_t* y_in, int64_t stride_in, int32_t* x_out,
+                      int32_t* y_out, int64_t stride_out, uint32_t* moved, uint8_t* goal,
+                      void* stream) {
+  clear_error();
+  const int rc = check_common(e, n_states, nullptr, puzzle, stride_in, 0);
+  if (rc != PW_OK) return rc;
+  PW_RETURN_IF_EMPTY(n_states);
+  if (stride_out < 4 * n_states) return set_error(PW_E_INVALID, "stride_out smaller than 4*N");
+  if (index == nullptr || x_in == nullptr || y_in == nullptr || x_out == nullptr || y_out == nullptr)
+    return set_error(PW_E_INVALID, "index / state pointer is NULL");
+  DeviceGuard guard(e->device);
+  ExpandParams p{};
+  p.blob = e->d_blob;
+  p.puzzle_off = e->d_off;
+  p.N = n_states;
+  p.puzzle_id = nullptr;
+  p.puzzle_uniform = puzzle;
+  p.uniform_u64 = e->puzzles[(size_t)puzzle].size_u64;
+  p.n_max = e->n_max;
+  p.index = index;
+  p.x_in = x_in;
+  p.y_in = y_in;
+  p.stride_in = stride_in;
+  p.x_out = x_out;
+  p.y_out = y_out;
+  p.stride_out = stride_out;
+  p.moved = moved;
+  p.goal = goal;
+  const cudaError_t err = launch_expand(p, e->puzzles[(size_t)puzzle].n, static_cast<cudaStream_t>(stream));
+  return err == cudaSuccess ? PW_OK : cuda_error(err, "pw_expand_indexed");
+}
+
+int pw_visited_insert(PwEngine* e, int puzzle, const int32_t* x, const int32_t* y, int64_t stride,
+                      int64_t first_id, int64_t count, const uint8_t* valid, uint64_t* table,
+                      int64_t capacity, uint8_t* is_new, void* stream) {
+  clear_error();
+  const int rc = check_common(e, count, nullptr, puzzle, stride, 0);
+  if (rc != PW_OK) return rc;
+  PW_RETURN_IF_EMPTY(count);
+  if (x == nullptr || y == nullptr || table == nullptr || is_new == nullptr)
+    return set_error(PW_E_INVALID, "NULL argument");
+  if (capacity <= 0 || (capacity & (capacity - 1)) != 0)
+    return set_error(PW_E_INVALID, "capacity must be a power of two");
+  if (first_id < 0 || first_id + count > stride || first_id + count >= ((int64_t)1 << 40))
+    return set_error(PW_E_INVALID, "state ids outside the arena");
+  DeviceGuard guard(e->device);
+  VisitedParams p{};
+  p.blob = e->d_blob;
+  p.puzzle_off = e->d_off;
+  p.puzzle = puzzle;
+  p.x = x;
+  p.y = y;
+  p.stride = stride;
+  p.first_id = first_id;
+  p.count = count;
+  p.valid = valid;
+  p.table = reinterpret_cast<unsigned long long*>(table);
+  p.capacity = capacity;
+  p.is_new = is_new;
+  p.status = e->d_status;
+  const cudaError_t err = launch_visited(p, static_cast<cudaStream_t>(stream));
+  return err == cudaSuccess ? PW_OK : cuda_error(err, "pw_visited_insert");
+}
+
 static int render_common(PwEngine* e, int64_t n_envs, const int32_t* puzzle_id, int puzzle_uniform,
                          const int32_t* x, const int32_t* y, int64_t stride, void* out, int dtype,
                          int ppc, int bw, int pad_h, int pad_w, const StepParams* fused,

@@ -53,6 +53,7 @@ struct ExpandParams {
   int32_t puzzle_uniform;
   int32_t uniform_u64;
   int32_t n_max;
+  const int64_t* index;  // optional: state e is column index[e] of x_in / y_in
   const int32_t* x_in;
   const int32_t* y_in;
   int64_t stride_in;
@@ -90,6 +91,21 @@ struct GoalParams {
   uint8_t* is_goal;
 };
 
+struct VisitedParams {
+  const uint64_t* blob;
+  const uint32_t* puzzle_off;
+  int32_t puzzle;
+  const int32_t* x;
+  const int32_t* y;
+  int64_t stride;
+  int64_t first_id, count;
+  const uint8_t* valid;
+  unsigned long long* table;
+  int64_t capacity;
+  uint8_t* is_new;
+  unsigned long long* status;
+};
+
 struct RenderParams {
   const uint64_t* blob;
   const uint32_t* puzzle_off;
@@ -116,6 +132,7 @@ cudaError_t launch_steps(const StepParams& p, int n_limit, cudaStream_t stream);
 cudaError_t launch_expand(const ExpandParams& p, int n_limit, cudaStream_t stream);
 cudaError_t launch_reset(const ResetParams& p, cudaStream_t stream);
 cudaError_t launch_goals(const GoalParams& p, cudaStream_t stream);
+cudaError_t launch_visited(const VisitedParams& p, cudaStream_t stream);
 cudaError_t launch_render(const RenderParams& p, const StepParams* fused_step, int n_limit,
                           cudaStream_t stream);
 cudaError_t upload_palette(const uint8_t* rgb, const float* rgb_f32, int n_colors);

@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(kBlock)
 // ------------------------------------------------------------------------------------------
 template <class Env>
 __device__ __forceinline__ void run_expand(Env& env, const ExpandParams& p, int64_t e) {
-  env.load(p.x_in, p.y_in, p.stride_in, e);
+  env.load(p.x_in, p.y_in, p.stride_in, p.index ? p.index[e] : e);
   const int g = env.g();
 #pragma unroll 1
   for (int a = 0; a < 4; ++a) {
@@ -317,6 +317,66 @@ __global__ void __launch_bounds__(kBlock) k_goals(const GoalParams p) {
   }
   if (p.achieved) p.achieved[e] = count;
   if (p.is_goal) p.is_goal[e] = count == g ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// visited set: open addressing, entry = fingerprint24 << 40 | (state id + 1); exact compare
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t mix64(uint64_t h) {  // splitmix64 finaliser
+  h ^= h >> 30;
+  h *= 0xbf58476d1ce4e5b9ull;
+  h ^= h >> 27;
+  h *= 0x94d049bb133111ebull;
+  h ^= h >> 31;
+  return h;
+}
+
+__global__ void __launch_bounds__(kBlock) k_visited_insert(const VisitedParams p) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.count) return;
+  if (p.valid && p.valid[i] == 0) {
+    p.is_new[i] = 0;
+    return;
+  }
+  const GlobalTable t{p.blob + p.puzzle_off[p.puzzle]};
+  const int n = (int)(t.word(kHdrCounts) & 0xffffu);
+  const int64_t id = p.first_id + i;
+  uint64_t h = 0x9e3779b97f4a7c15ull;
+  for (int j = 0; j < n; ++j) {
+    const uint64_t v = ((uint64_t)(uint32_t)p.x[j * p.stride + id] << 32) | (uint32_t)p.y[j * p.stride + id];
+    h = mix64(h ^ v) + 0x9e3779b97f4a7c15ull;
+  }
+  const uint64_t fp = (h >> 40) << 40;
+  const unsigned long long mine = fp | (unsigned long long)(id + 1);
+  const uint64_t mask = (uint64_t)p.capacity - 1;
+  uint64_t slot = mix64(h) & mask;
+  uint8_t is_new = 0;
+  bool done = false;
+  for (int64_t probes = 0; probes < p.capacity && !done; ++probes) {
+    unsigned long long cur = p.table[slot];
+    if (cur == 0ull) {
+      cur = atomicCAS(&p.table[slot], 0ull, mine);
+      if (cur == 0ull) {
+        is_new = 1;
+        done = true;
+        break;
+      }
+    }
+    if ((cur >> 40) == (mine >> 40)) {  // same fingerprint: compare the states themselves
+      const int64_t other = (int64_t)(cur & ((1ull << 40) - 1ull)) - 1;
+      bool same = true;
+      for (int j = 0; j < n && same; ++j)
+        same = p.x[j * p.stride + id] == p.x[j * p.stride + other] &&
+               p.y[j * p.stride + id] == p.y[j * p.stride + other];
+      if (same) {
+        done = true;
+        break;
+      }
+    }
+    slot = (slot + 1) & mask;
+  }
+  if (!done && p.status) atomicAdd(&p.status[1], 1ull);  // table full
+  p.is_new[i] = is_new;
 }
 
 inline unsigned grid_for(int64_t n) { return (unsigned)((n + kBlock - 1) / kBlock); }
@@ -423,6 +483,12 @@ cudaError_t launch_reset(const ResetParams& p, cudaStream_t stream) {
 cudaError_t launch_goals(const GoalParams& p, cudaStream_t stream) {
   if (p.N == 0) return cudaSuccess;
   k_goals<<<grid_for(p.N), kBlock, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_visited(const VisitedParams& p, cudaStream_t stream) {
+  if (p.count == 0) return cudaSuccess;
+  k_visited_insert<<<grid_for(p.count), kBlock, 0, stream>>>(p);
   return cudaGetLastError();
 }
 

@@ -228,6 +228,49 @@ class Engine:
         )
         return xy_out, moved, goal
 
+    def expand_indexed(self, arena: torch.Tensor, puzzle: int, index: torch.Tensor, out_base: int,
+                       moved: torch.Tensor, goal: torch.Tensor) -> None:
+        """Expands the states ``arena[:, :, index]`` of a state arena ``[2, n_max, capacity]`` and
+        writes the ``4 * len(index)`` successors back into the arena at columns
+        ``out_base + a * len(index) + i`` (pw_expand_indexed)."""
+        cap = self._chk_state(arena)
+        n = index.numel()
+        self._chk(index, torch.int64, (n,), "index")
+        self._chk(moved, torch.int32, (4 * n,), "moved")
+        self._chk(goal, torch.uint8, (4 * n,), "goal")
+        if out_base < 0 or out_base + 4 * n > cap:
+            raise ValueError("successors do not fit the arena")
+        x_out = arena[0].data_ptr() + 4 * out_base
+        y_out = arena[1].data_ptr() + 4 * out_base
+        _lib.check(
+            self._lib.pw_expand_indexed(self._h, n, int(puzzle), index.data_ptr(), arena[0].data_ptr(),
+                                        arena[1].data_ptr(), cap, x_out, y_out, cap,
+                                        moved.data_ptr(), goal.data_ptr(), self._stream())
+        )
+
+    def visited_insert(self, arena: torch.Tensor, puzzle: int, first_id: int, count: int,
+                       table: torch.Tensor, is_new: torch.Tensor,
+                       valid: Optional[torch.Tensor] = None) -> None:
+        """Exact duplicate detection (pw_visited_insert): ``is_new[i] = 1`` iff state
+        ``first_id + i`` of the arena was not yet in ``table`` (int64 ``[capacity]``, power of
+        two, zero-initialised)."""
+        cap = self._chk_state(arena)
+        self._chk(table, torch.int64, (table.numel(),), "table")
+        self._chk(is_new, torch.uint8, (count,), "is_new")
+        if valid is not None:
+            self._chk(valid, torch.uint8, (count,), "valid")
+        _lib.check(
+            self._lib.pw_visited_insert(self._h, int(puzzle), arena[0].data_ptr(), arena[1].data_ptr(),
+                                        cap, int(first_id), int(count), _ptr(valid), table.data_ptr(),
+                                        table.numel(), is_new.data_ptr(), self._stream())
+        )
+
+    def poll_status(self):
+        """(invalid actions, visited-table overflows) since the last poll (synchronises)."""
+        status = (ctypes.c_uint64 * 4)()
+        _lib.check(self._lib.pw_engine_poll(self._h, status, self._stream()))
+        return int(status[0]), int(status[1])
+
     def _render_out(self, n, dtype, ppc, pad_cells, out):
         tdtype = torch.float32 if dtype == "float32" else torch.uint8
         shape = (n, pad_cells[0] * ppc, pad_cells[1] * ppc, 3)
