@@ -164,6 +164,21 @@ PW_API int pw_rollout(PwEngine* engine, int64_t n_envs, int32_t n_steps, const i
                uint8_t* truncated, int32_t* steps, int32_t max_steps, float* return_sum,
                uint64_t* counters, uint32_t flags, void* stream);
 
+/* pw_rollout with the episode handling of a vector environment done entirely on the device
+ * (SURVEY.md 8f-2): after a terminated or truncated step the environment draws a NEW puzzle
+ * uniformly from the engine's puzzles -- what PushWorldEnv.reset does with random.choice
+ * (gym_env.py:171-176) -- and restarts from that puzzle's initial state with steps = 0.
+ * The draw is a counter-based hash of (seed, environment index, episode number), so a rollout is
+ * reproducible and independent of launch geometry:
+ *     puzzle = mulhi32(splitmix64(seed ^ env * 0x9E3779B97F4A7C15 ^ episode * 0xD1B54A32D192ED03) >> 32,
+ *                      num_puzzles)
+ * puzzle_id[N] (mandatory here), steps[N] and episode[N] are read and updated in place. */
+PW_API int pw_rollout_episodes(PwEngine* engine, int64_t n_envs, int32_t n_steps, int32_t* puzzle_id,
+                        int32_t* x, int32_t* y, int64_t stride, const uint8_t* actions,
+                        float* reward, int8_t* dgoals, uint8_t* terminated, uint8_t* truncated,
+                        int32_t* steps, int32_t max_steps, float* return_sum, uint64_t* counters,
+                        uint64_t seed, uint32_t* episode, void* stream);
+
 /* Goal predicates of every environment's CURRENT state.
  * Replaces: PushWorldPuzzle.count_achieved_goals (puzzle.py:396-407) and is_goal_state
  * (puzzle.py:409-411) / satisfiesGoal (cpp/src/pushworld_puzzle.cc:462-469).

@@ -48,6 +48,12 @@ SIGNATURES = {
          c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_uint32,
          c_void_p],
     ),
+    "pw_rollout_episodes": (
+        c_int,
+        [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
+         c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_uint64, c_void_p,
+         c_void_p],
+    ),
     "pw_goals": (
         c_int,
         [c_void_p, c_int64, c_void_p, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p],

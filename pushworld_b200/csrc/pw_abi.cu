@@ -377,6 +377,50 @@ int pw_rollout(PwEngine* e, int64_t n_envs, int32_t n_steps, const int32_t* puzz
   return err == cudaSuccess ? PW_OK : cuda_error(err, "pw_rollout");
 }
 
+int pw_rollout_episodes(PwEngine* e, int64_t n_envs, int32_t n_steps, int32_t* puzzle_id, int32_t* x,
+                        int32_t* y, int64_t stride, const uint8_t* actions, float* reward,
+                        int8_t* dgoals, uint8_t* terminated, uint8_t* truncated, int32_t* steps,
+                        int32_t max_steps, float* return_sum, uint64_t* counters, uint64_t seed,
+                        uint32_t* episode, void* stream) {
+  clear_error();
+  if (puzzle_id == nullptr) return set_error(PW_E_INVALID, "puzzle_id is mandatory");
+  const int rc = check_common(e, n_envs, puzzle_id, 0, stride, n_envs);
+  if (rc != PW_OK) return rc;
+  PW_RETURN_IF_EMPTY(n_envs);
+  if (n_steps < 0) return set_error(PW_E_INVALID, "negative step count");
+  if (x == nullptr || y == nullptr || actions == nullptr || episode == nullptr || steps == nullptr)
+    return set_error(PW_E_INVALID, "x / y / actions / steps / episode is NULL");
+  DeviceGuard guard(e->device);
+  StepParams p{};
+  p.blob = e->d_blob;
+  p.puzzle_off = e->d_off;
+  p.N = n_envs;
+  p.T = n_steps;
+  p.puzzle_id = puzzle_id;
+  p.n_max = e->n_max;
+  p.board_bits = 1 << 30;
+  p.x = x;
+  p.y = y;
+  p.stride = stride;
+  p.actions = actions;
+  p.reward = reward;
+  p.dgoals = dgoals;
+  p.terminated = terminated;
+  p.truncated = truncated;
+  p.steps = steps;
+  p.max_steps = max_steps;
+  p.return_sum = return_sum;
+  p.counters = reinterpret_cast<unsigned long long*>(counters);
+  p.status = e->d_status;
+  p.flags = kFlagAutoreset | kFlagResample;
+  p.puzzle_id_mut = puzzle_id;
+  p.episode = episode;
+  p.seed = seed;
+  p.num_puzzles = (int32_t)e->puzzles.size();
+  const cudaError_t err = launch_steps(p, e->n_max, static_cast<cudaStream_t>(stream));
+  return err == cudaSuccess ? PW_OK : cuda_error(err, "pw_rollout_episodes");
+}
+
 int pw_step(PwEngine* e, int64_t n_envs, const int32_t* puzzle_id, int puzzle_uniform, int32_t* x,
             int32_t* y, int64_t stride, const uint8_t* action, float* reward, int8_t* dgoals,
             uint8_t* terminated, uint8_t* truncated, int32_t* steps, int32_t max_steps,

@@ -50,6 +50,8 @@ struct EnvBase {
     awall_off_ = (int)t.word(kHdrAwallOff);
     desc_word_ = (int)t.word(kHdrObjOff) * 2;
   }
+  // points the view at another puzzle's table (same address space)
+  __device__ __forceinline__ void retarget(const uint64_t* base) { init_header(Table{base}); }
   __device__ __forceinline__ int n() const { return n_; }
   __device__ __forceinline__ int g() const { return g_; }
   __device__ __forceinline__ int width() const { return w_; }

@@ -6,6 +6,7 @@
 namespace pw {
 
 constexpr uint32_t kFlagAutoreset = 1u;
+constexpr uint32_t kFlagResample = 2u;  // autoreset draws a new puzzle (pw_rollout_episodes)
 
 // Host-precomputed static boards of a bitboard-eligible puzzle (pw_board.cuh), one per puzzle.
 struct BoardStaticPod {
@@ -43,6 +44,11 @@ struct StepParams {
   unsigned long long* counters;  // [4] or nullptr
   unsigned long long* status;    // engine status block
   uint32_t flags;
+  // pw_rollout_episodes only
+  int32_t* puzzle_id_mut;
+  uint32_t* episode;
+  uint64_t seed;
+  int32_t num_puzzles;
 };
 
 struct ExpandParams {

@@ -131,6 +131,7 @@ struct BoardSim {
 #pragma unroll
     for (int k = 0; k < NMAX; ++k) s.b[k] = st.init[k];
   }
+  __device__ __forceinline__ void resample(const StepParams&, int64_t) { load_initial(); }  // single puzzle
   __device__ __forceinline__ uint32_t do_step(int a) { return board_step(s, a, st.act); }
   __device__ __forceinline__ int achieved() const { return board_achieved(s); }
   __device__ __forceinline__ int goals() const { return s.g; }
@@ -391,6 +392,10 @@ cudaError_t launch_steps(const StepParams& p, int n_limit, cudaStream_t stream) 
   const unsigned grid = grid_for(p.N);
   const size_t state_bytes = (size_t)p.n_max * 2 * kBlock * sizeof(int);
   const bool lean = is_lean(p);
+  if (p.flags & kFlagResample) {  // puzzles change mid-rollout: dynamic-n policy, global tables
+    k_steps_mixed<0, false><<<grid, kBlock, state_bytes, stream>>>(p);
+    return cudaGetLastError();
+  }
 #define PW_GO(kernel, smem_bytes)                                         \
   do {                                                                    \
     if (lean)                                                             \

@@ -18,6 +18,20 @@ struct StepCounts {
   uint32_t terminated = 0, moved = 0, dgoals = 0, invalid = 0;
 };
 
+__device__ __forceinline__ uint64_t splitmix64(uint64_t h) {
+  h += 0x9e3779b97f4a7c15ull;
+  h = (h ^ (h >> 30)) * 0xbf58476d1ce4e5b9ull;
+  h = (h ^ (h >> 27)) * 0x94d049bb133111ebull;
+  return h ^ (h >> 31);
+}
+
+// The puzzle an environment plays in its `episode`-th episode (pw_rollout_episodes).
+__device__ __forceinline__ int draw_puzzle(uint64_t seed, int64_t env, uint32_t episode, int num_puzzles) {
+  const uint64_t h = splitmix64(seed ^ ((uint64_t)env * 0x9e3779b97f4a7c15ull) ^
+                                ((uint64_t)episode * 0xd1b54a32d192ed03ull));
+  return (int)(((h >> 32) * (uint64_t)num_puzzles) >> 32);
+}
+
 // Adaptor: an Env policy (pw_env.cuh) driven by the general rule of pw_core.cuh.
 template <class Env>
 struct GeneralSim {
@@ -28,6 +42,15 @@ struct GeneralSim {
   __device__ __forceinline__ uint32_t do_step(int a) { return step(env, a); }
   __device__ __forceinline__ int achieved() const { return achieved_goals(env); }
   __device__ __forceinline__ int goals() const { return env.g(); }
+  // new episode on a freshly drawn puzzle (only table views that can be re-pointed support it)
+  __device__ __forceinline__ void resample(const StepParams& p, int64_t e) {
+    const uint32_t episode = p.episode[e] + 1u;
+    p.episode[e] = episode;
+    const int pid = draw_puzzle(p.seed, e, episode, p.num_puzzles);
+    p.puzzle_id_mut[e] = pid;
+    env.retarget(p.blob + p.puzzle_off[pid]);
+    env.load_initial();
+  }
   static constexpr bool kCheapAchieved = false;
   static constexpr int kPrefetch = 1;
 };
@@ -42,7 +65,7 @@ __device__ __forceinline__ void run_steps_sim(Sim& sim, const StepParams& p, int
   int prev = sim.achieved();
   int steps = (!kLean && p.steps) ? p.steps[e] : 0;
   float ret = 0.f;
-  const int g = sim.goals();
+  int g = sim.goals();
   const int64_t N = p.N;
   const int T = p.T;
   // lean launches have T * N < 2^32 (is_lean), so one 32-bit element offset addresses all arrays
@@ -96,7 +119,12 @@ __device__ __forceinline__ void run_steps_sim(Sim& sim, const StepParams& p, int
         if (p.moved) p.moved[idx] = moved;
         ret += r;
         if ((p.flags & kFlagAutoreset) && (term || trunc)) {
-          sim.load_initial();
+          if (p.flags & kFlagResample) {
+            sim.resample(p, e);
+            g = sim.goals();
+          } else {
+            sim.load_initial();
+          }
           prev = sim.achieved();
           steps = 0;
         }

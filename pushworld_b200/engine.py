@@ -29,6 +29,17 @@ class StepOutput:
     moved: Optional[torch.Tensor] = None  # uint32 as int32 bit pattern, pw_step only
 
 
+def draw_puzzle(seed: int, env: int, episode: int, num_puzzles: int) -> int:
+    """Host mirror of the device generator used by pw_rollout_episodes (include/pushworld_b200.h)."""
+    m = (1 << 64) - 1
+    h = (seed ^ (env * 0x9E3779B97F4A7C15) ^ (episode * 0xD1B54A32D192ED03)) & m
+    h = (h + 0x9E3779B97F4A7C15) & m
+    h = ((h ^ (h >> 30)) * 0xBF58476D1CE4E5B9) & m
+    h = ((h ^ (h >> 27)) * 0x94D049BB133111EB) & m
+    h ^= h >> 31
+    return ((h >> 32) * num_puzzles) >> 32
+
+
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
@@ -191,6 +202,40 @@ class Engine:
                                  _ptr(truncated), _ptr(steps), int(max_steps or 0), _ptr(return_sum),
                                  _ptr(counters), _lib.PW_FLAG_AUTORESET if autoreset else 0,
                                  self._stream())
+        )
+
+    def rollout_episodes(self, xy: torch.Tensor, puzzle_id: torch.Tensor, actions: torch.Tensor,
+                         steps: torch.Tensor, episode: torch.Tensor, seed: int,
+                         max_steps: Optional[int] = None, reward: Optional[torch.Tensor] = None,
+                         terminated: Optional[torch.Tensor] = None, dgoals: Optional[torch.Tensor] = None,
+                         truncated: Optional[torch.Tensor] = None,
+                         return_sum: Optional[torch.Tensor] = None,
+                         counters: Optional[torch.Tensor] = None) -> None:
+        """T fused steps with on-device episode handling (pw_rollout_episodes): a terminated or
+        truncated environment draws a new puzzle (see ``draw_puzzle``) and restarts; ``puzzle_id``
+        (int32 [N]), ``steps`` (int32 [N]) and ``episode`` (int32 [N], used as uint32) are updated
+        in place."""
+        n = self._chk_state(xy)
+        self._chk(puzzle_id, torch.int32, (n,), "puzzle_id")
+        t = actions.shape[0]
+        self._chk(actions, torch.uint8, (t, n), "actions")
+        self._chk(steps, torch.int32, (n,), "steps")
+        self._chk(episode, torch.int32, (n,), "episode")
+        for name, ten, dt in (("reward", reward, torch.float32), ("terminated", terminated, torch.uint8),
+                              ("dgoals", dgoals, torch.int8), ("truncated", truncated, torch.uint8)):
+            if ten is not None:
+                self._chk(ten, dt, (t, n), name)
+        if return_sum is not None:
+            self._chk(return_sum, torch.float32, (n,), "return_sum")
+        if counters is not None:
+            self._chk(counters, torch.int64, (4,), "counters")
+        _lib.check(
+            self._lib.pw_rollout_episodes(self._h, n, t, puzzle_id.data_ptr(), xy[0].data_ptr(),
+                                          xy[1].data_ptr(), n, actions.data_ptr(), _ptr(reward),
+                                          _ptr(dgoals), _ptr(terminated), _ptr(truncated),
+                                          steps.data_ptr(), int(max_steps or 0), _ptr(return_sum),
+                                          _ptr(counters), int(seed) & (2**64 - 1), episode.data_ptr(),
+                                          self._stream())
         )
 
     def goals(self, xy: torch.Tensor, puzzle: PuzzleSel):

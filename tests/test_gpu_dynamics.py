@@ -333,3 +333,55 @@ def test_argument_errors(setup):
     rc = lib.pw_step(engine._h, 4, None, 10**6, xy[0].data_ptr(), xy[1].data_ptr(), 4, None,
                      None, None, None, None, None, 0, None, None)
     assert rc == _lib.PW_E_INVALID and b"puzzle_uniform" in lib.pw_last_error()
+
+
+def test_rollout_episodes_resamples_puzzles_like_the_host_model(golden):
+    """pw_rollout_episodes: on termination / truncation an environment draws a new puzzle with
+    the documented counter-based generator and restarts; the whole trajectory must equal a host
+    simulation with the oracle (reward, terminated, truncated per step; final puzzle, episode,
+    step counter and state)."""
+    from pushworld_b200.engine import Engine, draw_puzzle
+
+    names = ["trivial", "multiple_goals", "transitive_pushing", "pushing", "trivial_obstacle",
+             "trivial_tool", "file_parsing"]
+    texts = [golden.text("python3/" + n) for n in names]
+    engine = Engine(texts)
+    oracles = [po.OraclePuzzle(t) for t in texts]
+    n, T, max_steps, seed = 48, 160, 9, 0xC0FFEE1234
+    rng = np.random.default_rng(21)
+    actions = rng.integers(0, 4, size=(T, n), dtype=np.uint8)
+    pid0 = rng.integers(0, len(texts), size=n).astype(np.int32)
+    puzzle_id = torch.from_numpy(pid0.copy()).cuda()
+    xy = engine.new_state(n)
+    engine.reset(xy, puzzle_id)
+    steps = torch.zeros(n, dtype=torch.int32, device="cuda")
+    episode = torch.zeros(n, dtype=torch.int32, device="cuda")
+    reward = torch.empty((T, n), dtype=torch.float32, device="cuda")
+    term = torch.empty((T, n), dtype=torch.uint8, device="cuda")
+    trunc = torch.empty((T, n), dtype=torch.uint8, device="cuda")
+    engine.rollout_episodes(xy, puzzle_id, torch.from_numpy(actions).cuda(), steps, episode, seed,
+                            max_steps=max_steps, reward=reward, terminated=term, truncated=trunc)
+    r, te, tr = reward.cpu().numpy(), term.cpu().numpy(), trunc.cpu().numpy()
+    final, fpid = xy.cpu().numpy(), puzzle_id.cpu().numpy()
+    fsteps, fep = steps.cpu().numpy(), episode.cpu().numpy()
+    n_resets = 0
+    for e in range(n):
+        pid, ep, st = int(pid0[e]), 0, 0
+        state = oracles[pid].initial_state
+        for t in range(T):
+            nxt = oracles[pid].get_next_state(state, int(actions[t, e]))
+            rew, terminated, _ = po.step_reward(oracles[pid], state, nxt)
+            st += 1
+            truncated = st >= max_steps
+            assert np.float32(rew) == r[t, e] and terminated == bool(te[t, e]) and truncated == bool(tr[t, e]), (e, t)
+            state = nxt
+            if terminated or truncated:
+                ep += 1
+                pid = draw_puzzle(seed, e, ep, len(texts))
+                state, st = oracles[pid].initial_state, 0
+                n_resets += 1
+        assert (fpid[e], fep[e], fsteps[e]) == (pid, ep, st), e
+        got = tuple((int(final[0, j, e]), int(final[1, j, e])) for j in range(oracles[pid].num_objects))
+        assert got == state, e
+    assert n_resets > n * 10
+    assert len(set(fpid.tolist())) > 3  # the draw really spreads over the puzzles
