@@ -172,21 +172,36 @@ PW_HD uint32_t board_step(Board<NMAX, Word>& s, int action, const BoardAction<Wo
     m[k] = (Word)((Word)(s.b[k] << sl) >> sr);
     stop[k] = (Word)((m[k] & (k == 0 ? s.awall : s.wall)) | (s.b[k] & edge));
   }
-  Word u = m[0], hit = 0;
+  const bool agent_ok = au <= 3u && stop[0] == 0;  // puzzle.py:353-354
   uint32_t pushed = 1u;
-  bool grow = au <= 3u && stop[0] == 0;  // puzzle.py:353-354
-  const bool agent_ok = grow;
-  while (grow) {
-    const uint32_t before = pushed;
+  Word hit = 0;
+  if (NMAX == 2) {
+    // one pushable object: it is pushed iff the moved agent touches it
+    const bool p1 = (m[0] & s.b[1]) != 0;
+    hit = p1 ? stop[1] : (Word)0;
+    pushed |= p1 ? 2u : 0u;
+  } else if (NMAX == 3) {
+    // two pushable objects: direct pushes plus one level of chaining closes the set
+    const bool d1 = (m[0] & s.b[1]) != 0, d2 = (m[0] & s.b[2]) != 0;
+    const bool p2 = d2 || (d1 && (m[1] & s.b[2]) != 0);
+    const bool p1 = d1 || (p2 && (m[2] & s.b[1]) != 0);
+    hit = (Word)((p1 ? stop[1] : (Word)0) | (p2 ? stop[2] : (Word)0));
+    pushed |= (p1 ? 2u : 0u) | (p2 ? 4u : 0u);
+  } else {
+    Word u = m[0];
+    bool grow = agent_ok;
+    while (grow) {
+      const uint32_t before = pushed;
 #pragma unroll
-    for (int j = 1; j < NMAX; ++j) {
-      if ((u & s.b[j]) != 0) {  // b[j] == 0 for j >= n
-        u |= m[j];
-        hit |= stop[j];  // transitive stopping, puzzle.py:376-379
-        pushed |= 1u << j;
+      for (int j = 1; j < NMAX; ++j) {
+        if ((u & s.b[j]) != 0) {  // b[j] == 0 for j >= n
+          u |= m[j];
+          hit |= stop[j];  // transitive stopping, puzzle.py:376-379
+          pushed |= 1u << j;
+        }
       }
+      grow = pushed != before;
     }
-    grow = pushed != before;
   }
   pushed = (agent_ok && hit == 0) ? pushed : 0u;
 #pragma unroll
@@ -198,7 +213,10 @@ template <int NMAX, typename Word>
 PW_HD int board_achieved(const Board<NMAX, Word>& s) {  // puzzle.py:396-407
   int count = 0;
 #pragma unroll
-  for (int k = 0; k + 1 < NMAX; ++k) count += (s.b[k + 1] == s.goal[k]) ? 1 : 0;
+  for (int k = 0; k + 1 < NMAX; ++k) {
+    if (k >= s.g) break;  // uniform across the launch: a branch, not a wasted compare
+    count += (s.b[k + 1] == s.goal[k]) ? 1 : 0;
+  }
   return count;
 }
 

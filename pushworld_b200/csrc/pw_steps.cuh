@@ -74,7 +74,6 @@ __device__ __forceinline__ void run_steps_sim(Sim& sim, const StepParams& p, int
   const uint8_t* __restrict__ actions = p.actions;
   float* __restrict__ reward = p.reward;
   uint8_t* __restrict__ terminated = p.terminated;
-  const float r_plain = c_reward_lut[kMaxObjects];  // -0.01f
   // Actions are independent of the state, so they are fetched kPrefetch steps ahead: with ~8
   // warps per scheduler a single step of look-ahead does not cover the DRAM latency.
   constexpr int kPrefetch = Sim::kPrefetch;  // 1 for the (large) general rule: unrolling it thrashes the I-cache
@@ -97,9 +96,7 @@ __device__ __forceinline__ void run_steps_sim(Sim& sim, const StepParams& p, int
       const int dg = ach - prev;
       prev = ach;
       // gym_env.py:212-221; the float64 value (dg - 0.01) was rounded to float32 once, on the host
-      float r = r_plain;
-      if (dg != 0) r = c_reward_lut[dg + kMaxObjects];
-      r = term ? 10.0f : r;
+      const float r = term ? 10.0f : c_reward_lut[dg + kMaxObjects];
       if (term) ++c.terminated;
       if (moved) ++c.moved;
       c.dgoals += (uint32_t)max(dg, 0);

@@ -69,14 +69,14 @@ struct HostPos {
   int y(int j) const { return py[j]; }
 };
 
-template <typename Word>
-static int board_walk(const uint64_t* blob, int* x, int* y, const uint8_t* actions, int n_actions,
-                      int* xs, int* ys, uint32_t* moved, int* achieved) {
+template <typename Word, int NMAX>
+static int board_walk_n(const uint64_t* blob, int* x, int* y, const uint8_t* actions, int n_actions,
+                        int* xs, int* ys, uint32_t* moved, int* achieved) {
   HostTable t{blob};
   const int W = t.word(pw::kHdrDims) & 0xffff, H = t.word(pw::kHdrDims) >> 16;
   const int n = t.word(pw::kHdrCounts) & 0xffff;
-  if (pw::board_bits(W, H) > (int)sizeof(Word) * 8 || n > 8) return -1;
-  pw::Board<8, Word> s;
+  if (pw::board_bits(W, H) > (int)sizeof(Word) * 8 || n > NMAX) return -1;
+  pw::Board<NMAX, Word> s;
   pw::board_init(s, t);
   if (!pw::board_load(s, t, [&](int k) { return x[k]; }, [&](int k) { return y[k]; })) return -2;
   pw::BoardAction<Word> lut[4];
@@ -88,6 +88,16 @@ static int board_walk(const uint64_t* blob, int* x, int* y, const uint8_t* actio
       pw::board_position<Word>(s.b[k], s.P, &xs[(size_t)i * n + k], &ys[(size_t)i * n + k]);
   }
   return n;
+}
+
+// exact-n instantiations like the kernels' (2 and 3 objects use closed-form closures)
+template <typename Word>
+static int board_walk(const uint64_t* blob, int* x, int* y, const uint8_t* actions, int n_actions,
+                      int* xs, int* ys, uint32_t* moved, int* achieved) {
+  const int n = reinterpret_cast<const uint32_t*>(blob)[pw::kHdrCounts] & 0xffff;
+  if (n <= 2) return board_walk_n<Word, 2>(blob, x, y, actions, n_actions, xs, ys, moved, achieved);
+  if (n == 3) return board_walk_n<Word, 3>(blob, x, y, actions, n_actions, xs, ys, moved, achieved);
+  return board_walk_n<Word, 8>(blob, x, y, actions, n_actions, xs, ys, moved, achieved);
 }
 
 extern "C" {
