@@ -74,60 +74,71 @@ __device__ __forceinline__ void run_steps_sim(Sim& sim, const StepParams& p, int
   const uint8_t* __restrict__ actions = p.actions;
   float* __restrict__ reward = p.reward;
   uint8_t* __restrict__ terminated = p.terminated;
-  // Actions are independent of the state, so they are fetched kPrefetch steps ahead: with ~8
-  // warps per scheduler a single step of look-ahead does not cover the DRAM latency.
+  // Actions are independent of the state, so a whole group of kPrefetch steps is fetched one
+  // group ahead (double buffering in registers): the loads of group g+1 are issued before the
+  // steps of group g run, which covers the DRAM latency even at ~8 warps per scheduler.
   constexpr int kPrefetch = Sim::kPrefetch;  // 1 for the (large) general rule: unrolling it thrashes the I-cache
-  int ring[kPrefetch];
+  int ring[kPrefetch], nxt[kPrefetch];
+  auto fetch = [&](int t) -> int {  // action of step t (clamped to the last step)
+    const int tt = t < T ? t : T - 1;
+    return kLean ? actions[(uint32_t)e + (uint32_t)tt * n32] : actions[(int64_t)tt * N + e];
+  };
 #pragma unroll
-  for (int k = 0; k < kPrefetch; ++k)
-    ring[k] = k < T ? (kLean ? actions[off + (uint32_t)k * n32] : actions[(int64_t)k * N + e]) : 0;
-  for (int t0 = 0; t0 < T; t0 += kPrefetch) {
-#pragma unroll
-    for (int k = 0; k < kPrefetch; ++k) {
-      const int t = t0 + k;
-      if (t >= T) break;
-      const int a = ring[k];
-      if (t + kPrefetch < T)
-        ring[k] = kLean ? actions[off + (uint32_t)kPrefetch * n32]
-                        : actions[(int64_t)(t + kPrefetch) * N + e];
-      const uint32_t moved = sim.do_step(a);
-      const int ach = Sim::kCheapAchieved ? sim.achieved() : (moved ? sim.achieved() : prev);
-      const bool term = ach == g;  // puzzle.py:409-411
-      const int dg = ach - prev;
-      prev = ach;
-      // gym_env.py:212-221; the float64 value (dg - 0.01) was rounded to float32 once, on the host
-      const float r = term ? 10.0f : c_reward_lut[dg + kMaxObjects];
-      if (term) ++c.terminated;
-      if (moved) ++c.moved;
-      c.dgoals += (uint32_t)max(dg, 0);
-      if ((unsigned)a > 3u) ++c.invalid;
-      if (kLean) {
-        reward[off] = r;
-        terminated[off] = term ? 1 : 0;
-        off += n32;
-      } else {
-        const int64_t idx = (int64_t)t * N + e;
-        ++steps;
-        const bool trunc = p.max_steps > 0 && steps >= p.max_steps;  // gym_env.py:223
-        if (p.reward) p.reward[idx] = r;
-        if (p.dgoals) p.dgoals[idx] = (int8_t)dg;
-        if (p.terminated) p.terminated[idx] = term ? 1 : 0;
-        if (p.truncated) p.truncated[idx] = trunc ? 1 : 0;
-        if (p.moved) p.moved[idx] = moved;
-        ret += r;
-        if ((p.flags & kFlagAutoreset) && (term || trunc)) {
-          if (p.flags & kFlagResample) {
-            sim.resample(p, e);
-            g = sim.goals();
-          } else {
-            sim.load_initial();
-          }
-          prev = sim.achieved();
-          steps = 0;
+  for (int k = 0; k < kPrefetch; ++k) ring[k] = fetch(k);
+  auto one_step = [&](const int t, const int k) {
+    const int a = ring[k];
+    const uint32_t moved = sim.do_step(a);
+    const bool bad_action = (unsigned)a > 3u;
+    const int ach = Sim::kCheapAchieved ? sim.achieved() : (moved ? sim.achieved() : prev);
+    const bool term = ach == g;  // puzzle.py:409-411
+    const int dg = ach - prev;
+    prev = ach;
+    // gym_env.py:212-221; the float64 value (dg - 0.01) was rounded to float32 once, on the host
+    const float r = term ? 10.0f : c_reward_lut[dg + kMaxObjects];
+    if (term) ++c.terminated;
+    if (moved) ++c.moved;
+    c.dgoals += (uint32_t)max(dg, 0);
+    if (bad_action) ++c.invalid;
+    if (kLean) {
+      reward[off] = r;
+      terminated[off] = term ? 1 : 0;
+      off += n32;
+    } else {
+      const int64_t idx = (int64_t)t * N + e;
+      ++steps;
+      const bool trunc = p.max_steps > 0 && steps >= p.max_steps;  // gym_env.py:223
+      if (p.reward) p.reward[idx] = r;
+      if (p.dgoals) p.dgoals[idx] = (int8_t)dg;
+      if (p.terminated) p.terminated[idx] = term ? 1 : 0;
+      if (p.truncated) p.truncated[idx] = trunc ? 1 : 0;
+      if (p.moved) p.moved[idx] = moved;
+      ret += r;
+      if ((p.flags & kFlagAutoreset) && (term || trunc)) {
+        if (p.flags & kFlagResample) {
+          sim.resample(p, e);
+          g = sim.goals();
+        } else {
+          sim.load_initial();
         }
+        prev = sim.achieved();
+        steps = 0;
       }
     }
+  };
+  // full groups of kPrefetch steps: straight-line, no exits, so the ring lives in fixed registers
+  int t0 = 0;
+  for (; t0 + kPrefetch <= T; t0 += kPrefetch) {
+#pragma unroll
+    for (int k = 0; k < kPrefetch; ++k) nxt[k] = fetch(t0 + kPrefetch + k);
+#pragma unroll
+    for (int k = 0; k < kPrefetch; ++k) one_step(t0 + k, k);
+#pragma unroll
+    for (int k = 0; k < kPrefetch; ++k) ring[k] = nxt[k];
   }
+  // remainder (< kPrefetch steps): their actions are already in slots 0, 1, ...
+#pragma unroll
+  for (int k = 0; k + 1 < kPrefetch; ++k)
+    if (t0 + k < T) one_step(t0 + k, k);
   sim.store(p, e);
   if (!kLean) {
     if (p.steps) p.steps[e] = steps;
