@@ -62,6 +62,7 @@ struct PwEngine {
   unsigned long long* d_status = nullptr;  // [4]
   pw::BoardStaticPod* d_board_static = nullptr;  // [num_puzzles]
   std::vector<int> board_bits;                    // per puzzle, 1 << 30 = not eligible
+  int board_bits_all = 1 << 30;                   // max over all puzzles (mixed board kernel)
 };
 
 using namespace pw;
@@ -224,6 +225,8 @@ int pw_engine_create(const void* blob, size_t blob_bytes, const uint32_t* offset
                       reinterpret_cast<const uint64_t*>(bytes) + offsets_u64[p], &pods[(size_t)p]);
     e->board_bits.push_back(pods[(size_t)p].bits);
   }
+  e->board_bits_all = 0;
+  for (int b : e->board_bits) e->board_bits_all = b > e->board_bits_all ? b : e->board_bits_all;
 
   DeviceGuard guard(device);
   cudaError_t err = cudaSetDevice(device);
@@ -355,8 +358,8 @@ int pw_rollout(PwEngine* e, int64_t n_envs, int32_t n_steps, const int32_t* puzz
   p.puzzle_uniform = puzzle_id ? 0 : puzzle_uniform;
   p.uniform_u64 = puzzle_id ? 0 : e->puzzles[(size_t)puzzle_uniform].size_u64;
   p.n_max = e->n_max;
-  p.board_bits = puzzle_id ? (1 << 30) : e->board_bits[(size_t)puzzle_uniform];
-  p.board_static = puzzle_id ? nullptr : e->d_board_static + puzzle_uniform;
+  p.board_bits = puzzle_id ? e->board_bits_all : e->board_bits[(size_t)puzzle_uniform];
+  p.board_static = puzzle_id ? e->d_board_static : e->d_board_static + puzzle_uniform;
   p.x = x;
   p.y = y;
   p.stride = stride;
@@ -398,7 +401,8 @@ int pw_rollout_episodes(PwEngine* e, int64_t n_envs, int32_t n_steps, int32_t* p
   p.T = n_steps;
   p.puzzle_id = puzzle_id;
   p.n_max = e->n_max;
-  p.board_bits = 1 << 30;
+  p.board_bits = e->board_bits_all;
+  p.board_static = e->d_board_static;
   p.x = x;
   p.y = y;
   p.stride = stride;
@@ -441,8 +445,8 @@ int pw_step(PwEngine* e, int64_t n_envs, const int32_t* puzzle_id, int puzzle_un
   p.puzzle_uniform = puzzle_id ? 0 : puzzle_uniform;
   p.uniform_u64 = puzzle_id ? 0 : e->puzzles[(size_t)puzzle_uniform].size_u64;
   p.n_max = e->n_max;
-  p.board_bits = puzzle_id ? (1 << 30) : e->board_bits[(size_t)puzzle_uniform];
-  p.board_static = puzzle_id ? nullptr : e->d_board_static + puzzle_uniform;
+  p.board_bits = puzzle_id ? e->board_bits_all : e->board_bits[(size_t)puzzle_uniform];
+  p.board_static = puzzle_id ? e->d_board_static : e->d_board_static + puzzle_uniform;
   p.x = x;
   p.y = y;
   p.stride = stride;
@@ -656,8 +660,8 @@ int pw_step_render(PwEngine* e, int64_t n_envs, const int32_t* puzzle_id, int pu
   p.puzzle_uniform = puzzle_id ? 0 : puzzle_uniform;
   p.uniform_u64 = puzzle_id ? 0 : e->puzzles[(size_t)puzzle_uniform].size_u64;
   p.n_max = e->n_max;
-  p.board_bits = puzzle_id ? (1 << 30) : e->board_bits[(size_t)puzzle_uniform];
-  p.board_static = puzzle_id ? nullptr : e->d_board_static + puzzle_uniform;
+  p.board_bits = puzzle_id ? e->board_bits_all : e->board_bits[(size_t)puzzle_uniform];
+  p.board_static = puzzle_id ? e->d_board_static : e->d_board_static + puzzle_uniform;
   p.x = x;
   p.y = y;
   p.stride = stride;

@@ -137,6 +137,14 @@ PW_HD void board_position(Word board, int P, int* x, int* y) {
   *y = r + 1;
 }
 
+PW_HD uint32_t pick_byte(uint32_t packed, uint32_t index) {  // byte `index` (0..3) of `packed`
+#if defined(__CUDA_ARCH__)
+  return __byte_perm(packed, 0u, index | 0x4440u);
+#else
+  return (packed >> (8u * index)) & 0xffu;
+#endif
+}
+
 // Per-action constants, looked up by action index (kept in shared memory by the kernels):
 // shift amounts (RIGHT / DOWN move towards higher bits, LEFT / UP towards lower bits,
 // puzzle.py:43-50) and the edge row a vertical move would leave the interior through.
@@ -161,9 +169,28 @@ PW_HD void board_action_table(const Board<NMAX, Word>& s, BoardAction<Word>* lut
 // no "already pushed" bookkeeping is needed) and sweeps repeat until the pushed set stops
 // growing.  Obstacles hit by any pushed object are accumulated and tested once at the end.
 template <int NMAX, typename Word>
+PW_HD uint32_t board_step(Board<NMAX, Word>& s, int action, const BoardAction<Word> act);
+
+// The per-action constants computed from the board itself (no table): used when every thread
+// plays a different puzzle and a shared look-up table is not available.
+template <int NMAX, typename Word>
+PW_HD BoardAction<Word> board_action_of(const Board<NMAX, Word>& s, uint32_t a2) {
+  const uint32_t P = (uint32_t)s.P;
+  BoardAction<Word> act;
+  act.sl = pick_byte((1u << 8) | (P << 24), a2);
+  act.sr = pick_byte(1u | (P << 16), a2);
+  act.edge = a2 == 2u ? s.edge_up : (a2 == 3u ? s.edge_down : (Word)0);
+  return act;
+}
+
+template <int NMAX, typename Word>
 PW_HD uint32_t board_step(Board<NMAX, Word>& s, int action, const BoardAction<Word>* lut) {
+  return board_step(s, action, lut[(uint32_t)action & 3u]);
+}
+
+template <int NMAX, typename Word>
+PW_HD uint32_t board_step(Board<NMAX, Word>& s, int action, const BoardAction<Word> act) {
   const uint32_t au = (uint32_t)action;
-  const BoardAction<Word> act = lut[au & 3u];
   const uint32_t sl = act.sl, sr = act.sr;
   const Word edge = act.edge;
   Word m[NMAX], stop[NMAX];

@@ -198,6 +198,97 @@ __global__ void __launch_bounds__(kBlock, MIN_BLOCKS)
   flush_counts(c, p, s_counters);
 }
 
+// ------------------------------------------------------------------------------------------
+// Bitboard kernel for per-environment puzzle ids (e.g. a batch over the 15,400 level-0 puzzles):
+// every puzzle of the engine is board-eligible, so each thread loads its own puzzle's static
+// boards (host-precomputed BoardStaticPod, L2 resident) into registers and computes the action
+// constants from its pitch.  pw_rollout_episodes re-points a thread at a freshly drawn puzzle.
+// ------------------------------------------------------------------------------------------
+template <int NMAX, typename Word>
+struct BoardSimMixed {
+  static constexpr bool kCheapAchieved = true;
+  static constexpr int kPrefetch = 4;
+  Board<NMAX, Word>& s;
+  const BoardStaticPod* pod;
+  __device__ __forceinline__ void load_static(const BoardStaticPod* q) {
+    pod = q;
+    s.wall = (Word)__ldg(&q->wall);
+    s.awall = (Word)__ldg(&q->awall);
+    s.edge_up = (Word)__ldg(&q->edge_up);
+    s.edge_down = (Word)__ldg(&q->edge_down);
+    s.P = __ldg(&q->P);
+    s.n = __ldg(&q->n);
+    s.g = __ldg(&q->g);
+#pragma unroll
+    for (int k = 0; k < NMAX; ++k) s.goal[k] = (Word)__ldg(&q->goal[k]);
+  }
+  __device__ __forceinline__ void store(const StepParams& p, int64_t e) {
+#pragma unroll
+    for (int k = 0; k < NMAX; ++k)
+      if (k < s.n) {
+        int x, y;
+        board_position<Word>(s.b[k], s.P, &x, &y);
+        p.x[k * p.stride + e] = x;
+        p.y[k * p.stride + e] = y;
+      }
+  }
+  __device__ __forceinline__ void load_initial() {
+#pragma unroll
+    for (int k = 0; k < NMAX; ++k) s.b[k] = (Word)__ldg(&pod->init[k]);
+  }
+  __device__ __forceinline__ void resample(const StepParams& p, int64_t e) {
+    const uint32_t episode = p.episode[e] + 1u;
+    p.episode[e] = episode;
+    const int pid = draw_puzzle(p.seed, e, episode, p.num_puzzles);
+    p.puzzle_id_mut[e] = pid;
+    load_static(p.board_static + pid);
+    load_initial();
+  }
+  __device__ __forceinline__ uint32_t do_step(int a) {
+    return board_step(s, a, board_action_of(s, (uint32_t)a & 3u));
+  }
+  __device__ __forceinline__ int achieved() const { return board_achieved(s); }
+  __device__ __forceinline__ int goals() const { return s.g; }
+};
+
+__device__ __noinline__ void general_slow_path_global(const uint64_t* table, const StepParams& p,
+                                                      int64_t e, StepCounts& c) {
+  LocalEnv<GlobalTable> env;
+  env.init(GlobalTable{table});
+  run_steps_thread<false>(env, p, e, c);
+}
+
+template <int NMAX, typename Word, int MIN_BLOCKS, bool kLean>
+__global__ void __launch_bounds__(kBlock, MIN_BLOCKS)
+    k_steps_board_mixed(const __grid_constant__ StepParams p) {
+  __shared__ uint32_t s_counters[4];
+  if (threadIdx.x < 4) s_counters[threadIdx.x] = 0;
+  __syncthreads();
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  StepCounts c;
+  if (e < p.N) {
+    const int pid = p.puzzle_id[e];
+    const GlobalTable tbl{p.blob + p.puzzle_off[pid]};
+    Board<NMAX, Word> s;
+    BoardSimMixed<NMAX, Word> sim{s, nullptr};
+    sim.load_static(p.board_static + pid);
+    const bool regular = board_load(s, tbl, [&](int k) { return p.x[k * p.stride + e]; },
+                                    [&](int k) { return p.y[k * p.stride + e]; });
+    // episode handling re-points the thread at other puzzles: stay on boards (all eligible)
+    if (regular) {
+      run_steps_sim<kLean>(sim, p, e, c);
+    } else if (!(p.flags & kFlagResample)) {
+      general_slow_path_global(tbl.base, p, e, c);
+    } else {
+      // an irregular state under episode handling: general rule with re-pointable tables
+      LocalEnv<GlobalTable> env;
+      env.init(tbl);
+      run_steps_thread<false>(env, p, e, c);
+    }
+  }
+  flush_counts(c, p, s_counters);
+}
+
 // Per-environment puzzle ids: tables are read from global memory (L1/L2 resident, the whole
 // benchmark set is < 1 MB).
 template <int NMAX, bool kLean>
@@ -392,6 +483,26 @@ cudaError_t launch_steps(const StepParams& p, int n_limit, cudaStream_t stream) 
   const unsigned grid = grid_for(p.N);
   const size_t state_bytes = (size_t)p.n_max * 2 * kBlock * sizeof(int);
   const bool lean = is_lean(p);
+  if (p.puzzle_id != nullptr && p.board_bits <= 64 && n_limit <= 8) {
+    // every puzzle of the engine is board-eligible: per-thread boards (also under episode handling)
+    const bool w32 = p.board_bits <= 32;
+#define PW_BOARD_MIXED(NB, MINB)                                                                  \
+  do {                                                                                            \
+    if (w32 && lean)                                                                              \
+      k_steps_board_mixed<NB, uint32_t, MINB, true><<<grid, kBlock, 0, stream>>>(p);              \
+    else if (w32)                                                                                 \
+      k_steps_board_mixed<NB, uint32_t, MINB, false><<<grid, kBlock, 0, stream>>>(p);             \
+    else if (lean)                                                                                \
+      k_steps_board_mixed<NB, uint64_t, MINB, true><<<grid, kBlock, 0, stream>>>(p);              \
+    else                                                                                          \
+      k_steps_board_mixed<NB, uint64_t, MINB, false><<<grid, kBlock, 0, stream>>>(p);             \
+  } while (0)
+    if (n_limit <= 3) PW_BOARD_MIXED(3, 8);
+    else if (n_limit <= 5) PW_BOARD_MIXED(5, 8);
+    else PW_BOARD_MIXED(8, 6);
+#undef PW_BOARD_MIXED
+    return cudaGetLastError();
+  }
   if (p.flags & kFlagResample) {  // puzzles change mid-rollout: dynamic-n policy, global tables
     k_steps_mixed<0, false><<<grid, kBlock, state_bytes, stream>>>(p);
     return cudaGetLastError();

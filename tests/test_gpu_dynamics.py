@@ -335,15 +335,22 @@ def test_argument_errors(setup):
     assert rc == _lib.PW_E_INVALID and b"puzzle_uniform" in lib.pw_last_error()
 
 
-def test_rollout_episodes_resamples_puzzles_like_the_host_model(golden):
+@pytest.mark.parametrize("names", [
+    # general rule (file_parsing does not fit a 64-bit board)
+    ["trivial", "multiple_goals", "transitive_pushing", "pushing", "trivial_obstacle", "trivial_tool",
+     "file_parsing"],
+    # every puzzle fits a uint64 board: per-thread bitboard kernel
+    ["trivial", "multiple_goals", "transitive_pushing", "pushing", "trivial_obstacle", "trivial_tool"],
+    # every puzzle fits a uint32 board
+    ["trivial", "multiple_goals", "transitive_pushing", "pushing", "trivial_obstacle"],
+])
+def test_rollout_episodes_resamples_puzzles_like_the_host_model(golden, names):
     """pw_rollout_episodes: on termination / truncation an environment draws a new puzzle with
     the documented counter-based generator and restarts; the whole trajectory must equal a host
     simulation with the oracle (reward, terminated, truncated per step; final puzzle, episode,
     step counter and state)."""
     from pushworld_b200.engine import Engine, draw_puzzle
 
-    names = ["trivial", "multiple_goals", "transitive_pushing", "pushing", "trivial_obstacle",
-             "trivial_tool", "file_parsing"]
     texts = [golden.text("python3/" + n) for n in names]
     engine = Engine(texts)
     oracles = [po.OraclePuzzle(t) for t in texts]
@@ -385,3 +392,52 @@ def test_rollout_episodes_resamples_puzzles_like_the_host_model(golden):
         assert got == state, e
     assert n_resets > n * 10
     assert len(set(fpid.tolist())) > 3  # the draw really spreads over the puzzles
+
+
+def test_mixed_bitboard_kernel_matches_oracle_and_handles_irregular_inputs(golden):
+    """An engine whose puzzles all fit one machine word runs per-environment puzzle ids on the
+    per-thread bitboard kernel; plain rollouts, T=1 steps and states that are NOT regular (two
+    objects on one cell: general-rule slow path inside the same launch) must all match the oracle."""
+    from pushworld_b200.engine import Engine
+
+    names = ["trivial", "multiple_goals", "transitive_pushing", "pushing", "trivial_obstacle"]
+    texts = [golden.text("python3/" + n) for n in names]
+    engine = Engine(texts)
+    oracles = [po.OraclePuzzle(t) for t in texts]
+    rng = np.random.default_rng(33)
+    n, T = 96, 120
+    pids = rng.integers(0, len(texts), size=n).astype(np.int32)
+    puzzle_id = torch.from_numpy(pids).cuda()
+    states = []
+    for e in range(n):
+        o = oracles[pids[e]]
+        st = o.initial_state
+        for _ in range(int(rng.integers(0, 30))):
+            st = o.get_next_state(st, int(rng.integers(4)))
+        if e % 7 == 3 and o.num_objects >= 3:  # irregular: object 2 dropped onto object 1
+            st = st[:2] + (st[1],) + st[3:]
+        states.append(st)
+    actions = rng.integers(0, 5, size=(T, n)).astype(np.uint8)  # 4 = invalid -> no-op
+    xy = engine.state_from_tuples(states)
+    reward = torch.empty((T, n), dtype=torch.float32, device="cuda")
+    term = torch.empty((T, n), dtype=torch.uint8, device="cuda")
+    engine.rollout(xy, puzzle_id, torch.from_numpy(actions).cuda(), reward=reward, terminated=term)
+    xy1 = engine.state_from_tuples(states)
+    out1 = engine.step(xy1, puzzle_id, torch.from_numpy(actions[0]).cuda(), want_moved=True)
+    final, r, te = xy.cpu().numpy(), reward.cpu().numpy(), term.cpu().numpy()
+    first, moved1 = xy1.cpu().numpy(), out1.moved.cpu().numpy()
+    for e in range(n):
+        o = oracles[pids[e]]
+        st = states[e]
+        for t in range(T):
+            a = int(actions[t, e])
+            nxt, moved_idx = (st, []) if a > 3 else o.get_next_state_and_moved(st, a)
+            rr, tt, _ = po.step_reward(o, st, nxt)
+            assert np.float32(rr) == r[t, e] and tt == bool(te[t, e]), (e, t)
+            if t == 0:
+                got = tuple((int(first[0, j, e]), int(first[1, j, e])) for j in range(o.num_objects))
+                assert got == nxt and int(moved1[e]) == sum(1 << k for k in moved_idx), e
+            st = nxt
+        got = tuple((int(final[0, j, e]), int(final[1, j, e])) for j in range(o.num_objects))
+        assert got == st, e
+    assert engine.poll_invalid_actions() == int((actions > 3).sum()) + int((actions[0] > 3).sum())
