@@ -116,6 +116,47 @@ def main():
         results.append(rollout_case("cfg3 rollout: 223 puzzles interleaved (e mod 223), 2^18 x 256",
                                     eng, interleaved, n, 256, 1235))
 
+    if want("level0"):
+        # RL-style mixed batch: 2048 synthetic level-0-like puzzles (5x5 interior, 3 objects, as in the
+        # reference's level0.zip), per-environment puzzle ids, on-device episode handling
+        rng = np.random.default_rng(2026)
+        texts = []
+        while len(texts) < 2048:
+            cells = [["." for _ in range(5)] for _ in range(5)]
+            free = [(x, y) for x in range(5) for y in range(5)]
+            rng.shuffle(free)
+            for name, (x, y) in zip(["a", "m0", "g0", "m1", "w", "w"], free):
+                cells[y][x] = name
+            texts.append("\n".join(" ".join(r) for r in cells) + "\n")
+        eng = Engine(texts, device=dev)
+        n, T = 1 << 18, 256
+        ids = torch.randint(0, len(texts), (n,), dtype=torch.int32, device=dev)
+        gen = torch.Generator(device=dev).manual_seed(77)
+        actions = torch.randint(0, 4, (T, n), dtype=torch.uint8, device=dev, generator=gen)
+        reward = torch.empty((T, n), dtype=torch.float32, device=dev)
+        term = torch.empty((T, n), dtype=torch.uint8, device=dev)
+        xy = eng.new_state(n)
+
+        def run_plain():
+            eng.reset(xy, ids)
+            eng.rollout(xy, ids, actions, reward=reward, terminated=term)
+
+        ms = time_ms(run_plain)
+        results.append(report("level0-like mixed batch (2048 puzzles, random ids), rollout 2^18 x 256",
+                              n * T, ms, 6.0 + 16.0 * 3 / T, {"unit": "env-steps"}))
+        steps = torch.zeros(n, dtype=torch.int32, device=dev)
+        episode = torch.zeros(n, dtype=torch.int32, device=dev)
+        pid = ids.clone()
+
+        def run_episodes():
+            eng.rollout_episodes(xy, pid, actions, steps, episode, seed=5, max_steps=100,
+                                 reward=reward, terminated=term)
+
+        eng.reset(xy, pid)
+        ms = time_ms(run_episodes)
+        results.append(report("level0-like mixed batch, rollout_episodes (max_steps=100, re-sampling)",
+                              n * T, ms, 6.0 + 16.0 * 3 / T, {"unit": "env-steps"}))
+
     if want("cfg4"):
         key = "level2/Pull Dont Push"
         eng = Engine([data.puzzle_text(key)], device=dev)
