@@ -111,28 +111,52 @@ struct BoardStatic {
   int P, n, g;
 };
 
+// Writes the positions back.  After a single step (pw_step) only the pushed objects changed, by
+// the action's displacement: update those in place instead of re-deriving every position from its
+// board (which costs an integer division per object).
+template <int NMAX, typename Word>
+__device__ __forceinline__ void board_store(const Board<NMAX, Word>& s, const StepParams& p, int64_t e,
+                                            uint32_t last_moved, int last_action) {
+  if (p.T == 1 && !(p.flags & kFlagAutoreset)) {
+    const int dx = action_dx(last_action), dy = action_dy(last_action);
+#pragma unroll
+    for (int k = 0; k < NMAX; ++k)
+      if ((last_moved >> k) & 1u) {
+        if (dx) p.x[k * p.stride + e] += dx;
+        if (dy) p.y[k * p.stride + e] += dy;
+      }
+    return;
+  }
+#pragma unroll
+  for (int k = 0; k < NMAX; ++k)
+    if (k < s.n) {
+      int x, y;
+      board_position<Word>(s.b[k], s.P, &x, &y);
+      p.x[k * p.stride + e] = x;
+      p.y[k * p.stride + e] = y;
+    }
+}
+
 template <int NMAX, typename Word>
 struct BoardSim {
   static constexpr bool kCheapAchieved = true;
   static constexpr int kPrefetch = 4;
   Board<NMAX, Word>& s;
   const BoardStatic<Word>& st;
+  uint32_t last_moved = 0;
+  int last_action = 0;
   __device__ __forceinline__ void store(const StepParams& p, int64_t e) {
-#pragma unroll
-    for (int k = 0; k < NMAX; ++k)
-      if (k < s.n) {
-        int x, y;
-        board_position<Word>(s.b[k], s.P, &x, &y);
-        p.x[k * p.stride + e] = x;
-        p.y[k * p.stride + e] = y;
-      }
+    board_store(s, p, e, last_moved, last_action);
   }
   __device__ __forceinline__ void load_initial() {
 #pragma unroll
     for (int k = 0; k < NMAX; ++k) s.b[k] = st.init[k];
   }
   __device__ __forceinline__ void resample(const StepParams&, int64_t) { load_initial(); }  // single puzzle
-  __device__ __forceinline__ uint32_t do_step(int a) { return board_step(s, a, st.act); }
+  __device__ __forceinline__ uint32_t do_step(int a) {
+    last_action = a;
+    return last_moved = board_step(s, a, st.act);
+  }
   __device__ __forceinline__ int achieved() const { return board_achieved(s); }
   __device__ __forceinline__ int goals() const { return s.g; }
 };
@@ -189,7 +213,7 @@ __global__ void __launch_bounds__(kBlock, MIN_BLOCKS)
     const bool regular = board_load(s, tbl, [&](int k) { return p.x[k * p.stride + e]; },
                                     [&](int k) { return p.y[k * p.stride + e]; });
     if (regular) {
-      BoardSim<NMAX, Word> sim{s, st};
+      BoardSim<NMAX, Word> sim{s, st, 0u, 0};
       run_steps_sim<kLean>(sim, p, e, c);
     } else {
       general_slow_path(smem, p, e, c);
@@ -210,6 +234,8 @@ struct BoardSimMixed {
   static constexpr int kPrefetch = 4;
   Board<NMAX, Word>& s;
   const BoardStaticPod* pod;
+  uint32_t last_moved = 0;
+  int last_action = 0;
   __device__ __forceinline__ void load_static(const BoardStaticPod* q) {
     pod = q;
     s.wall = (Word)__ldg(&q->wall);
@@ -223,14 +249,7 @@ struct BoardSimMixed {
     for (int k = 0; k < NMAX; ++k) s.goal[k] = (Word)__ldg(&q->goal[k]);
   }
   __device__ __forceinline__ void store(const StepParams& p, int64_t e) {
-#pragma unroll
-    for (int k = 0; k < NMAX; ++k)
-      if (k < s.n) {
-        int x, y;
-        board_position<Word>(s.b[k], s.P, &x, &y);
-        p.x[k * p.stride + e] = x;
-        p.y[k * p.stride + e] = y;
-      }
+    board_store(s, p, e, last_moved, last_action);
   }
   __device__ __forceinline__ void load_initial() {
 #pragma unroll
@@ -245,7 +264,8 @@ struct BoardSimMixed {
     load_initial();
   }
   __device__ __forceinline__ uint32_t do_step(int a) {
-    return board_step(s, a, board_action_of(s, (uint32_t)a & 3u));
+    last_action = a;
+    return last_moved = board_step(s, a, board_action_of(s, (uint32_t)a & 3u));
   }
   __device__ __forceinline__ int achieved() const { return board_achieved(s); }
   __device__ __forceinline__ int goals() const { return s.g; }
@@ -270,7 +290,7 @@ __global__ void __launch_bounds__(kBlock, MIN_BLOCKS)
     const int pid = p.puzzle_id[e];
     const GlobalTable tbl{p.blob + p.puzzle_off[pid]};
     Board<NMAX, Word> s;
-    BoardSimMixed<NMAX, Word> sim{s, nullptr};
+    BoardSimMixed<NMAX, Word> sim{s, nullptr, 0u, 0};
     sim.load_static(p.board_static + pid);
     const bool regular = board_load(s, tbl, [&](int k) { return p.x[k * p.stride + e]; },
                                     [&](int k) { return p.y[k * p.stride + e]; });
