@@ -99,7 +99,8 @@ class PushWorldNativeError(RuntimeError):
 
 
 def library_path() -> str:
-    return _build.LIB_PATH
+    # PUSHWORLD_B200_LIB points at an alternative build of the same ABI (kernel experiments)
+    return os.environ.get("PUSHWORLD_B200_LIB") or _build.LIB_PATH
 
 
 def load(build_if_missing: bool = True) -> ctypes.CDLL:
@@ -108,7 +109,7 @@ def load(build_if_missing: bool = True) -> ctypes.CDLL:
     if _lib is not None:
         return _lib
     path = library_path()
-    if build_if_missing:
+    if build_if_missing and path == _build.LIB_PATH:
         try:
             _build.build()
         except Exception as exc:  # no nvcc on this machine: a prebuilt .so may still be there
