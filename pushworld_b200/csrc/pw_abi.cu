@@ -623,7 +623,6 @@ static int render_common(PwEngine* e, int64_t n_envs, const int32_t* puzzle_id, 
   p.out_w = pad_w * ppc;
   p.max_cells = e->max_cells;
   p.max_blob_u64 = e->max_blob_u64;
-  p.max_h = need_h;
   const cudaError_t err = launch_render(p, fused, n_limit_of(e, puzzle_id, puzzle_uniform),
                                         static_cast<cudaStream_t>(stream));
   return err == cudaSuccess ? PW_OK : cuda_error(err, what);

@@ -116,31 +116,8 @@ PW_HD bool static_blocked(const Env& env, uint32_t dj, int x, int y, int dx, int
 //   2. only for the (few) candidates the exact row-mask tests and the wall test of the pushee.
 // Without the split, lanes whose pushes happen at different j would each execute the heavy
 // path on their own.
-// Objects whose bounding box lies within one cell of the agent's bounding box: the only ones the
-// agent can push with ANY of the four actions.  Successor expansion computes this once per state
-// and restricts the agent's candidate search of all four steps to it.
 template <class Env>
-PW_HD uint32_t agent_neighbours(const Env& env) {
-  const int n = env.n();
-  const int jend = Env::kStaticN ? Env::kStaticN : n;
-  const uint32_t d0 = env.desc(0);
-  const int xa = env.x(0) - 1, ya = env.y(0) - 1;          // agent box grown by one cell
-  const int wa = desc_w(d0) + 2, ha = desc_h(d0) + 2;
-  uint32_t near = 0;
-#pragma unroll
-  for (int j = 1; j < jend; ++j) {
-    if (Env::kStaticN && j >= n) break;
-    const uint32_t dj = env.desc(j);
-    const int wj1 = desc_w(dj) - 1, hj1 = desc_h(dj) - 1;
-    const bool near_x = (unsigned)(env.x(j) - xa + wj1) < (unsigned)(wa + wj1);
-    const bool near_y = (unsigned)(env.y(j) - ya + hj1) < (unsigned)(ha + hj1);
-    near |= (near_x && near_y) ? (1u << j) : 0u;
-  }
-  return near;
-}
-
-template <class Env>
-PW_HD uint32_t step(Env& env, int action, uint32_t agent_near = 0xffffffffu) {
+PW_HD uint32_t step(Env& env, int action) {
   if ((unsigned)action > 3u) return 0;  // invalid actions are no-ops (counted by the caller)
   const int dx = action_dx(action), dy = action_dy(action);
   if (static_blocked(env, env.desc(0), env.x(0), env.y(0), dx, dy, env.awall_off())) return 0;
@@ -156,18 +133,14 @@ PW_HD uint32_t step(Env& env, int action, uint32_t agent_near = 0xffffffffu) {
     const int wi = desc_w(di), hi = desc_h(di);
     // phase 1: -w_j < x_j - xm < w_i  and  -h_j < y_j - ym < h_i, as two unsigned range checks
     uint32_t cand = 0;
-    if (i == 0 && agent_near != 0xffffffffu) {
-      cand = agent_near;  // superset computed once by the caller; phase 2 is exact
-    } else {
 #pragma unroll
-      for (int j = 1; j < jend; ++j) {
-        if (Env::kStaticN && j >= n) break;
-        const uint32_t dj = env.desc(j);
-        const int wj1 = desc_w(dj) - 1, hj1 = desc_h(dj) - 1;
-        const bool near_x = (unsigned)(env.x(j) - xm + wj1) < (unsigned)(wi + wj1);
-        const bool near_y = (unsigned)(env.y(j) - ym + hj1) < (unsigned)(hi + hj1);
-        cand |= (near_x && near_y) ? (1u << j) : 0u;
-      }
+    for (int j = 1; j < jend; ++j) {
+      if (Env::kStaticN && j >= n) break;
+      const uint32_t dj = env.desc(j);
+      const int wj1 = desc_w(dj) - 1, hj1 = desc_h(dj) - 1;
+      const bool near_x = (unsigned)(env.x(j) - xm + wj1) < (unsigned)(wi + wj1);
+      const bool near_y = (unsigned)(env.y(j) - ym + hj1) < (unsigned)(hi + hj1);
+      cand |= (near_x && near_y) ? (1u << j) : 0u;
     }
     cand &= ~pushed;
     // phase 2: exact tests for the candidates

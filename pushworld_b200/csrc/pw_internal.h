@@ -128,8 +128,6 @@ struct RenderParams {
   int32_t out_h, out_w;  // pixels
   int32_t max_cells;     // max width*height over the engine's puzzles
   int32_t max_blob_u64;
-  int32_t max_h;         // max height (cells) over the puzzles this launch can touch
-  int32_t pattern_sets;  // set by launch_render: 2 (double buffered) or >= max_h (whole frame)
 };
 
 cudaError_t upload_reward_lut(const float* host_lut);

@@ -342,10 +342,9 @@ template <class Env>
 __device__ __forceinline__ void run_expand(Env& env, const ExpandParams& p, int64_t e) {
   env.load(p.x_in, p.y_in, p.stride_in, p.index ? p.index[e] : e);
   const int g = env.g();
-  const uint32_t near = agent_neighbours(env);  // shared by the four actions (state is restored)
 #pragma unroll 1
   for (int a = 0; a < 4; ++a) {
-    const uint32_t moved = step(env, a, near);
+    const uint32_t moved = step(env, a);
     const int64_t s = (int64_t)a * p.N + e;
     env.store(p.x_out, p.y_out, p.stride_out, s);
     if (p.moved) p.moved[s] = moved;

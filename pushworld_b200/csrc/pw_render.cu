@@ -117,10 +117,10 @@ __global__ void __launch_bounds__(kRenderBlock) k_render(const RenderParams p, c
   uint16_t* s_xmap = reinterpret_cast<uint16_t*>(s_y + 32);  // out_w entries: cx << 2 | region
   const int row_bytes = p.out_w * 3 * (int)sizeof(T);
   const int row_pitch = (row_bytes + 15) & ~15;
-  // pattern_sets x 3 region rows (2 = double buffered, >= H = whole frame), then a zero row; 16-byte aligned
+  // 2 pattern sets (double buffered) x 3 region rows, then a zero row; 16-byte aligned
   uint8_t* s_pat = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(s_xmap + p.out_w) + 15) & ~static_cast<uintptr_t>(15));
-  uint8_t* s_zero = s_pat + p.pattern_sets * 3 * row_pitch;
+  uint8_t* s_zero = s_pat + 6 * row_pitch;
 
   if (threadIdx.x < 16) {
     s_pal_f[threadIdx.x] = make_float4(c_pal_f32[threadIdx.x][0], c_pal_f32[threadIdx.x][1],
@@ -213,26 +213,15 @@ __global__ void __launch_bounds__(kRenderBlock) k_render(const RenderParams p, c
     for (int Y = warp; Y < pad_top; Y += n_warps) emit(Y, s_zero);
     for (int Y = pad_top + img_h + warp; Y < p.out_h; Y += n_warps) emit(Y, s_zero);
     __syncthreads();  // codes ready
-    if (p.pattern_sets >= H) {
-      // small frames: the patterns of ALL cell rows fit in shared memory -> two barriers per frame
-      for (int cy = 0; cy < H; ++cy) build(cy, cy);
+    build(0, 0);
+    __syncthreads();
+    for (int cy = 0; cy < H; ++cy) {
+      if (cy + 1 < H) build(cy + 1, (cy + 1) & 1);  // next cell row while this one streams out
+      const uint8_t* set = s_pat + (cy & 1) * 3 * row_pitch;
+      const int Y0 = pad_top + cy * ppc;
+      for (int oy = warp; oy < ppc; oy += n_warps)
+        emit(Y0 + oy, set + region_of(oy, ppc, bw) * row_pitch);
       __syncthreads();
-      for (int Y = warp; Y < img_h; Y += n_warps) {
-        const int cy = Y / ppc, oy = Y - cy * ppc;
-        emit(pad_top + Y, s_pat + (cy * 3 + region_of(oy, ppc, bw)) * row_pitch);
-      }
-      __syncthreads();
-    } else {
-      build(0, 0);
-      __syncthreads();
-      for (int cy = 0; cy < H; ++cy) {
-        if (cy + 1 < H) build(cy + 1, (cy + 1) & 1);  // next cell row while this one streams out
-        const uint8_t* set = s_pat + (cy & 1) * 3 * row_pitch;
-        const int Y0 = pad_top + cy * ppc;
-        for (int oy = warp; oy < ppc; oy += n_warps)
-          emit(Y0 + oy, set + region_of(oy, ppc, bw) * row_pitch);
-        __syncthreads();
-      }
     }
   }
 }
@@ -245,13 +234,8 @@ cudaError_t launch_render(const RenderParams& p, const StepParams* fused_step, i
   if (p.N == 0) return cudaSuccess;
   const int elem = p.dtype == 1 ? 4 : 1;
   const size_t row_pitch = ((size_t)p.out_w * 3 * elem + 15) & ~(size_t)15;
-  const size_t fixed = (size_t)p.max_blob_u64 * 8 + (size_t)p.max_cells * 8 + 64 * sizeof(int) +
-                       (size_t)p.out_w * 2 + 16 + row_pitch;
-  // whole-frame pattern mode if the patterns of the tallest puzzle fit in ~40 KB (keeps >= 4 CTAs/SM)
-  RenderParams q = p;
-  q.pattern_sets = 2;
-  if ((size_t)p.max_h * 3 * row_pitch <= 40 * 1024) q.pattern_sets = p.max_h;
-  const size_t smem = fixed + (size_t)q.pattern_sets * 3 * row_pitch;
+  const size_t smem = (size_t)p.max_blob_u64 * 8 + (size_t)p.max_cells * 8 + 64 * sizeof(int) +
+                      (size_t)p.out_w * 2 + 16 + 7 * row_pitch;
   if (smem > kRenderMaxDynamicSmem) return cudaErrorInvalidValue;
   StepParams sp{};
   if (fused_step) sp = *fused_step;
@@ -267,7 +251,7 @@ cudaError_t launch_render(const RenderParams& p, const StepParams* fused_step, i
   int64_t want = (int64_t)sm_count * 16;
   if ((p.N + 3) / 4 > want) want = (p.N + 3) / 4;
   const unsigned grid = (unsigned)(p.N < want ? p.N : want);
-#define PW_LAUNCH(T, F) k_render<T, F><<<grid, kRenderBlock, smem, stream>>>(q, sp)
+#define PW_LAUNCH(T, F) k_render<T, F><<<grid, kRenderBlock, smem, stream>>>(p, sp)
   if (p.dtype == 1) {
     if (fused_step) PW_LAUNCH(float, true);
     else PW_LAUNCH(float, false);
