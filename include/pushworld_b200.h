@@ -220,6 +220,25 @@ PW_API int pw_visited_insert(PwEngine* engine, int puzzle, const int32_t* x, con
                       int64_t stride, int64_t first_id, int64_t count, const uint8_t* valid,
                       uint64_t* table, int64_t capacity, uint8_t* is_new, void* stream);
 
+/* Batched novelty measure of width-based search (Lipovetzky & Geffner 2017), the heuristic the
+ * reference's "N+RGD" planner mode combines with RGD (cpp/src/heuristics/novelty.cc:30-77,
+ * cpp/src/run_planner.cc:47-57).  `seen` is a caller-owned, zero-initialised bit table of
+ * pw_novelty_table_words() uint32 words holding, for the puzzle's n objects and C = width*height
+ * grid positions, one bit per (object, position) and one bit per (object i < object j,
+ * position_i, position_j).  For the `count` states with ids first_id .. first_id+count-1 of a
+ * state arena (see pw_visited_insert) and their moved-object masks (as written by pw_expand):
+ *   novelty[i] = 1  if a moved object is at a position never seen for that object,
+ *                2  else if a pair (moved object, any other object) is in an unseen combination,
+ *                3  otherwise (also when nothing moved),
+ * judged against the table as it was BEFORE the call; afterwards the positions / pairs of all
+ * `count` states are inserted.  With count = 1 per call this is exactly the reference's
+ * sequential algorithm; larger batches evaluate a whole search layer against the previous
+ * layers.  Objects outside the grid are ignored.  valid[i] == 0 (optional) skips a state. */
+PW_API int pw_novelty_table_words(const PwEngine* engine, int puzzle, uint64_t* n_words);
+PW_API int pw_novelty(PwEngine* engine, int puzzle, const int32_t* x, const int32_t* y, int64_t stride,
+               int64_t first_id, int64_t count, const uint32_t* moved, const uint8_t* valid,
+               uint32_t* seen, uint8_t* novelty, void* stream);
+
 /* RGB image of every environment's state.
  * Replaces: PushWorldPuzzle.render + _draw_object (puzzle.py:426-469,596-638) and, with
  * dtype F32 and padding, render_observation_padded (env_utils.py:44-91).

@@ -73,6 +73,12 @@ SIGNATURES = {
         [c_void_p, c_int, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p,
          c_int64, c_void_p, c_void_p],
     ),
+    "pw_novelty_table_words": (c_int, [c_void_p, c_int, POINTER(c_uint64)]),
+    "pw_novelty": (
+        c_int,
+        [c_void_p, c_int, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p,
+         c_void_p, c_void_p, c_void_p],
+    ),
     "pw_render": (
         c_int,
         [c_void_p, c_int64, c_void_p, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int,

@@ -588,6 +588,49 @@ int pw_visited_insert(PwEngine* e, int puzzle, const int32_t* x, const int32_t* 
   return err == cudaSuccess ? PW_OK : cuda_error(err, "pw_visited_insert");
 }
 
+static uint64_t novelty_bits(const PuzzleInfo& info) {
+  const uint64_t n = (uint64_t)info.n, c = (uint64_t)info.width * (uint64_t)info.height;
+  return n * c + n * (n - 1) / 2 * c * c;
+}
+
+int pw_novelty_table_words(const PwEngine* e, int puzzle, uint64_t* n_words) {
+  clear_error();
+  if (e == nullptr || n_words == nullptr) return set_error(PW_E_INVALID, "NULL argument");
+  if (puzzle < 0 || puzzle >= (int)e->puzzles.size())
+    return set_error(PW_E_INVALID, "puzzle out of range");
+  *n_words = (novelty_bits(e->puzzles[(size_t)puzzle]) + 31) / 32;
+  return PW_OK;
+}
+
+int pw_novelty(PwEngine* e, int puzzle, const int32_t* x, const int32_t* y, int64_t stride,
+               int64_t first_id, int64_t count, const uint32_t* moved, const uint8_t* valid,
+               uint32_t* seen, uint8_t* novelty, void* stream) {
+  clear_error();
+  const int rc = check_common(e, count, nullptr, puzzle, stride, 0);
+  if (rc != PW_OK) return rc;
+  PW_RETURN_IF_EMPTY(count);
+  if (x == nullptr || y == nullptr || moved == nullptr || seen == nullptr || novelty == nullptr)
+    return set_error(PW_E_INVALID, "NULL argument");
+  if (first_id < 0 || first_id + count > stride) return set_error(PW_E_INVALID, "state ids outside the arena");
+  DeviceGuard guard(e->device);
+  const PuzzleInfo& info = e->puzzles[(size_t)puzzle];
+  NoveltyParams p{};
+  p.x = x;
+  p.y = y;
+  p.stride = stride;
+  p.first_id = first_id;
+  p.count = count;
+  p.moved = moved;
+  p.valid = valid;
+  p.seen = seen;
+  p.novelty = novelty;
+  p.n = info.n;
+  p.width = info.width;
+  p.height = info.height;
+  const cudaError_t err = launch_novelty(p, static_cast<cudaStream_t>(stream));
+  return err == cudaSuccess ? PW_OK : cuda_error(err, "pw_novelty");
+}
+
 static int render_common(PwEngine* e, int64_t n_envs, const int32_t* puzzle_id, int puzzle_uniform,
                          const int32_t* x, const int32_t* y, int64_t stride, void* out, int dtype,
                          int ppc, int bw, int pad_h, int pad_w, const StepParams* fused,

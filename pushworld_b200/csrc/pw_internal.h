@@ -112,6 +112,18 @@ struct VisitedParams {
   unsigned long long* status;
 };
 
+struct NoveltyParams {
+  const int32_t* x;
+  const int32_t* y;
+  int64_t stride;
+  int64_t first_id, count;
+  const uint32_t* moved;
+  const uint8_t* valid;
+  uint32_t* seen;
+  uint8_t* novelty;
+  int32_t n, width, height;
+};
+
 struct RenderParams {
   const uint64_t* blob;
   const uint32_t* puzzle_off;
@@ -139,6 +151,7 @@ cudaError_t launch_expand(const ExpandParams& p, int n_limit, cudaStream_t strea
 cudaError_t launch_reset(const ResetParams& p, cudaStream_t stream);
 cudaError_t launch_goals(const GoalParams& p, cudaStream_t stream);
 cudaError_t launch_visited(const VisitedParams& p, cudaStream_t stream);
+cudaError_t launch_novelty(const NoveltyParams& p, cudaStream_t stream);
 cudaError_t launch_render(const RenderParams& p, const StepParams* fused_step, int n_limit,
                           cudaStream_t stream);
 cudaError_t upload_palette(const uint8_t* rgb, const float* rgb_f32, int n_colors);

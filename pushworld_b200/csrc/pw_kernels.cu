@@ -491,6 +491,67 @@ __global__ void __launch_bounds__(kBlock) k_visited_insert(const VisitedParams p
   p.is_new[i] = is_new;
 }
 
+// ------------------------------------------------------------------------------------------
+// novelty (cpp/src/heuristics/novelty.cc:30-77), batch semantics: test pass, then insert pass
+// bit layout: singles [i * C + pos_i], then pairs [base + (pair(i<j) * C + pos_i) * C + pos_j]
+// ------------------------------------------------------------------------------------------
+struct NoveltyIndex {
+  int n, W, H;
+  uint64_t C, pair_base;
+  __device__ __forceinline__ NoveltyIndex(const NoveltyParams& p)
+      : n(p.n), W(p.width), H(p.height), C((uint64_t)p.width * p.height), pair_base((uint64_t)p.n * C) {}
+  __device__ __forceinline__ int64_t pos(int x, int y) const {  // -1 outside the grid
+    return (x < 0 || y < 0 || x >= W || y >= H) ? -1 : (int64_t)y * W + x;
+  }
+  __device__ __forceinline__ uint64_t single(int i, int64_t pi) const { return (uint64_t)i * C + pi; }
+  __device__ __forceinline__ uint64_t pair(int i, int j, int64_t pi, int64_t pj) const {  // i < j
+    const uint64_t k = (uint64_t)i * (2 * n - i - 1) / 2 + (uint64_t)(j - i - 1);
+    return pair_base + (k * C + (uint64_t)pi) * C + (uint64_t)pj;
+  }
+};
+
+template <bool kInsert>
+__global__ void __launch_bounds__(kBlock) k_novelty(const NoveltyParams p) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= p.count) return;
+  if (p.valid && p.valid[s] == 0) {
+    if (!kInsert) p.novelty[s] = 3;
+    return;
+  }
+  const NoveltyIndex ix(p);
+  const int64_t id = p.first_id + s;
+  uint32_t moved = p.moved[s];
+  int novelty = 3;
+  while (moved) {
+    const int i = __ffs((int)moved) - 1;
+    moved &= moved - 1;
+    if (i >= p.n) break;
+    const int64_t pi = ix.pos(p.x[i * p.stride + id], p.y[i * p.stride + id]);
+    if (pi < 0) continue;
+    {
+      const uint64_t bit = ix.single(i, pi);
+      if (kInsert) {
+        atomicOr(&p.seen[bit >> 5], 1u << (bit & 31));
+      } else if (!((p.seen[bit >> 5] >> (bit & 31)) & 1u)) {
+        novelty = 1;
+      }
+    }
+    if (!kInsert && novelty == 1) continue;  // cannot get better; pairs are inserted by the other pass
+    for (int j = 0; j < p.n; ++j) {
+      if (j == i) continue;
+      const int64_t pj = ix.pos(p.x[j * p.stride + id], p.y[j * p.stride + id]);
+      if (pj < 0) continue;
+      const uint64_t bit = i < j ? ix.pair(i, j, pi, pj) : ix.pair(j, i, pj, pi);
+      if (kInsert) {
+        atomicOr(&p.seen[bit >> 5], 1u << (bit & 31));
+      } else if (novelty > 2 && !((p.seen[bit >> 5] >> (bit & 31)) & 1u)) {
+        novelty = 2;
+      }
+    }
+  }
+  if (!kInsert) p.novelty[s] = (uint8_t)novelty;
+}
+
 inline unsigned grid_for(int64_t n) { return (unsigned)((n + kBlock - 1) / kBlock); }
 
 }  // namespace
@@ -625,6 +686,13 @@ cudaError_t launch_goals(const GoalParams& p, cudaStream_t stream) {
 cudaError_t launch_visited(const VisitedParams& p, cudaStream_t stream) {
   if (p.count == 0) return cudaSuccess;
   k_visited_insert<<<grid_for(p.count), kBlock, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_novelty(const NoveltyParams& p, cudaStream_t stream) {
+  if (p.count == 0) return cudaSuccess;
+  k_novelty<false><<<grid_for(p.count), kBlock, 0, stream>>>(p);
+  k_novelty<true><<<grid_for(p.count), kBlock, 0, stream>>>(p);
   return cudaGetLastError();
 }
 

@@ -310,6 +310,32 @@ class Engine:
                                         table.numel(), is_new.data_ptr(), self._stream())
         )
 
+    def novelty_table(self, puzzle: int) -> torch.Tensor:
+        """A zeroed ``seen`` table (int32 words) for ``novelty`` on this puzzle."""
+        words = ctypes.c_uint64(0)
+        _lib.check(self._lib.pw_novelty_table_words(self._h, int(puzzle), ctypes.byref(words)))
+        return torch.zeros(int(words.value), dtype=torch.int32, device=self.device)
+
+    def novelty(self, arena: torch.Tensor, puzzle: int, first_id: int, count: int,
+                moved: torch.Tensor, seen: torch.Tensor, out: Optional[torch.Tensor] = None,
+                valid: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Novelty (1, 2 or 3) of ``count`` arena states given their moved-object masks, judged
+        against ``seen`` as it was before the call; the states are then inserted (pw_novelty)."""
+        cap = self._chk_state(arena)
+        self._chk(moved, torch.int32, (count,), "moved")
+        self._chk(seen, torch.int32, (seen.numel(),), "seen")
+        if out is None:
+            out = torch.empty(count, dtype=torch.uint8, device=self.device)
+        self._chk(out, torch.uint8, (count,), "novelty")
+        if valid is not None:
+            self._chk(valid, torch.uint8, (count,), "valid")
+        _lib.check(
+            self._lib.pw_novelty(self._h, int(puzzle), arena[0].data_ptr(), arena[1].data_ptr(), cap,
+                                 int(first_id), int(count), moved.data_ptr(), _ptr(valid),
+                                 seen.data_ptr(), out.data_ptr(), self._stream())
+        )
+        return out
+
     def poll_status(self):
         """(invalid actions, visited-table overflows) since the last poll (synchronises)."""
         status = (ctypes.c_uint64 * 4)()

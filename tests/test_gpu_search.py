@@ -84,3 +84,82 @@ def test_visited_insert_is_exact(golden):
     tiny = torch.zeros(64, dtype=torch.int64, device="cuda")
     engine.visited_insert(arena, 0, 0, len(dup), tiny, is_new)
     assert engine.poll_status()[1] > 0
+
+
+class _NoveltyModel:
+    """cpp/src/heuristics/novelty.cc:30-77 restated with python sets."""
+
+    def __init__(self, n):
+        self.singles = [set() for _ in range(n)]
+        self.pairs = {}
+        self.n = n
+
+    def evaluate(self, state, moved_idx, insert=True):
+        novelty = 3
+        new_singles, new_pairs = [], []
+        for i in moved_idx:
+            if state[i] not in self.singles[i]:
+                novelty = 1
+                new_singles.append((i, state[i]))
+            for j in range(self.n):
+                if j == i:
+                    continue
+                a, b = (i, j) if i < j else (j, i)
+                key = (a, b, state[a], state[b])
+                if key not in self.pairs:
+                    if novelty > 2:
+                        novelty = 2
+                    new_pairs.append(key)
+        if insert:
+            self.insert(new_singles, new_pairs)
+        return novelty, new_singles, new_pairs
+
+    def insert(self, singles, pairs):
+        for i, p in singles:
+            self.singles[i].add(p)
+        for key in pairs:
+            self.pairs[key] = True
+
+
+def test_novelty_sequential_and_batched(golden):
+    """pw_novelty with one state per call equals the reference's sequential algorithm; with a
+    batch per call it equals 'judge the whole batch against the previous table, then insert'."""
+    from pushworld_b200.engine import Engine
+
+    text = golden.text("benchmark/level2/Pull Dont Push")
+    engine = Engine([text])
+    oracle = po.OraclePuzzle(text)
+    rng = np.random.default_rng(12)
+    # a stream of (state, moved objects) as a search would produce them
+    stream = []
+    state = oracle.initial_state
+    for _ in range(1200):
+        nxt, moved_idx = oracle.get_next_state_and_moved(state, int(rng.integers(4)))
+        stream.append((nxt, moved_idx))
+        state = nxt if rng.random() < 0.9 else oracle.initial_state
+    arena = engine.state_from_tuples([s for s, _ in stream])
+    moved = torch.tensor([sum(1 << k for k in m) for _, m in stream], dtype=torch.int32, device="cuda")
+
+    # sequential: one state per call
+    seen = engine.novelty_table(0)
+    model = _NoveltyModel(oracle.num_objects)
+    for t in range(400):
+        got = int(engine.novelty(arena, 0, t, 1, moved[t:t + 1], seen).item())
+        want, _, _ = model.evaluate(*stream[t])
+        assert got == want, t
+
+    # batched: whole batches judged against the table before the call
+    seen = engine.novelty_table(0)
+    model = _NoveltyModel(oracle.num_objects)
+    for lo in range(0, len(stream), 96):
+        hi = min(len(stream), lo + 96)
+        got = engine.novelty(arena, 0, lo, hi - lo, moved[lo:hi].contiguous(), seen).cpu().numpy()
+        want, pending = [], []
+        for s, m in stream[lo:hi]:
+            nov, ns, nps = model.evaluate(s, m, insert=False)
+            want.append(nov)
+            pending.append((ns, nps))
+        for ns, nps in pending:
+            model.insert(ns, nps)
+        assert got.tolist() == want, lo
+    assert set(np.unique(got).tolist()) <= {1, 2, 3}
