@@ -310,6 +310,28 @@ def run_ours(args) -> None:
     assert torch.equal(h_rew[-1], out.reward[-1].cpu()) and torch.equal(h_term[-1], out.terminated[-1].cpu())
     chunks = (T_STEPS + 63) // 64
 
+    # ---- end to end, summaries only: host actions in, per-environment returns out ------
+    h_ret = torch.empty(N_ENVS, dtype=torch.float32).pin_memory()
+    h_nterm = torch.empty(N_ENVS, dtype=torch.int32).pin_memory()
+
+    def e2e_returns_step():
+        env.reset()
+        env.rollout_host_returns(h_act, h_ret, h_nterm, chunk_steps=64)
+
+    for _ in range(min(args.warmup, 3)):
+        e2e_returns_step()
+    distributed.barrier()
+    torch.cuda.synchronize()
+    r_start, r_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    r_start.record()
+    for _ in range(e2e_steps):
+        e2e_returns_step()
+    r_stop.record()
+    torch.cuda.synchronize()
+    e2e_ret_ms = distributed.max_over_ranks(r_start.elapsed_time(r_stop), dev)
+    e2e_ret_value = world * e2e_steps * N_ENVS * T_STEPS / (e2e_ret_ms * 1e-3)
+    assert torch.equal(h_nterm.to(torch.int64), out.terminated.sum(dim=0, dtype=torch.int64).cpu())
+
     if rank != 0:
         return
 
@@ -378,6 +400,15 @@ def run_ours(args) -> None:
             "d2h_bytes_per_step": T_STEPS * N_ENVS * 5,
             "ms_per_step": e2e_ms / e2e_steps,
             "api": "PushWorldVectorEnv.rollout_host (pinned host buffers, 3-stream pipeline)",
+        },
+        "e2e_summaries": {
+            "value": e2e_ret_value,
+            "unit": UNIT,
+            "h2d_bytes_per_step": T_STEPS * N_ENVS,
+            "d2h_bytes_per_step": N_ENVS * 8,
+            "ms_per_step": e2e_ret_ms / e2e_steps,
+            "api": "PushWorldVectorEnv.rollout_host_returns (per-environment return sum + terminated "
+            "count come back; per-step arrays stay on the device)",
         },
         "gpu_launches": 2 * args.steps,
         "gpu_launches_e2e": (1 + chunks) * e2e_steps,

@@ -248,6 +248,21 @@ class PushWorldVectorEnv:
         pipe = self._host_pipe(chunk_steps)
         pipe.run(self, actions, reward, terminated)
 
+    def rollout_host_returns(self, actions: torch.Tensor, returns: torch.Tensor,
+                             n_terminated: torch.Tensor, chunk_steps: int = 64) -> None:
+        """Host-buffer rollout that brings back only per-environment SUMMARIES: ``returns``
+        (float32 [N], sum of the T rewards) and ``n_terminated`` (int32 [N], number of steps with
+        terminated set) -- pinned host tensors, like ``actions`` (uint8 [T, N]).  The per-step
+        reward / terminated arrays stay on the device (``self.last_reward`` / ``self.last_terminated``
+        hold the last chunk), so the PCIe traffic is 1 byte per env-step in and 8 bytes per
+        environment out."""
+        self._require_reset()
+        t, n = actions.shape
+        assert n == self.num_envs and returns.shape == (n,) and n_terminated.shape == (n,)
+        assert actions.is_pinned() and returns.is_pinned() and n_terminated.is_pinned()
+        pipe = self._host_pipe(chunk_steps)
+        pipe.run_returns(self, actions, returns, n_terminated)
+
     def _host_pipe(self, chunk_steps: int):
         pipe = getattr(self, "_pipe", None)
         if pipe is None or pipe.chunk != chunk_steps:
@@ -304,5 +319,46 @@ class _HostPipe:
                 terminated[lo:hi].copy_(self.d_term[b][:m], non_blocking=True)
                 self.ev_out[b].record(self.s_out)
         cur.wait_stream(self.s_out)
+        cur.wait_stream(self.s_run)
+        cur.synchronize()
+
+    def run_returns(self, env: "PushWorldVectorEnv", actions, returns, n_terminated) -> None:
+        t, n = actions.shape
+        dev = env.device
+        cur = torch.cuda.current_stream(dev)
+        for s in (self.s_in, self.s_run):
+            s.wait_stream(cur)
+        if not hasattr(self, "d_ret"):
+            self.d_ret = torch.zeros(n, dtype=torch.float32, device=dev)
+            self.d_nterm = torch.zeros(n, dtype=torch.int32, device=dev)
+        n_chunks = (t + self.chunk - 1) // self.chunk
+        with torch.cuda.stream(self.s_run):
+            self.d_ret.zero_()
+            self.d_nterm.zero_()
+        for k in range(n_chunks):
+            b = k % self.DEPTH
+            lo, hi = k * self.chunk, min(t, (k + 1) * self.chunk)
+            m = hi - lo
+            with torch.cuda.stream(self.s_in):
+                if k >= self.DEPTH:
+                    self.s_in.wait_event(self.ev_run[b])
+                self.d_act[b][:m].copy_(actions[lo:hi], non_blocking=True)
+                self.ev_in[b].record(self.s_in)
+            with torch.cuda.stream(self.s_run):
+                self.s_run.wait_event(self.ev_in[b])
+                track = env.max_steps is not None or env.autoreset
+                env.engine.rollout(env.xy, env._sel, self.d_act[b][:m], reward=self.d_rew[b][:m],
+                                   terminated=self.d_term[b][:m], steps=env.steps if track else None,
+                                   max_steps=env.max_steps, return_sum=self.d_ret,
+                                   autoreset=env.autoreset)
+                # per-environment count of terminated steps (a column sum; device-side plumbing)
+                self.d_nterm += self.d_term[b][:m].sum(dim=0, dtype=torch.int32)
+                if not track:
+                    env.steps += m
+                self.ev_run[b].record(self.s_run)
+        with torch.cuda.stream(self.s_run):
+            returns.copy_(self.d_ret, non_blocking=True)
+            n_terminated.copy_(self.d_nterm, non_blocking=True)
+        env.last_reward, env.last_terminated = self.d_rew[(n_chunks - 1) % self.DEPTH], self.d_term[(n_chunks - 1) % self.DEPTH]
         cur.wait_stream(self.s_run)
         cur.synchronize()

@@ -120,3 +120,29 @@ def test_constructor_errors(golden, tmp_path):
         (tmp_path / f"p{i}.pwp").write_text(t)
     env = PushWorldVectorEnv(str(tmp_path), 10)
     assert env.engine.num_puzzles == len(texts)
+
+
+def test_rollout_host_returns_matches_dense_rollout(golden):
+    from pushworld_b200.vector_env import PushWorldVectorEnv
+
+    text = golden.text("benchmark/level1/Road Block")
+    n, T = 300, 150
+    env = PushWorldVectorEnv([text], n, puzzle_ids=0)
+    env.reset()
+    gen = torch.Generator(device="cuda").manual_seed(8)
+    actions = torch.randint(0, 4, (T, n), dtype=torch.uint8, device="cuda", generator=gen)
+    dense = env.rollout(actions, want_return=True)
+    final = env.xy.clone()
+    env.reset()
+    h_act = actions.cpu().pin_memory()
+    h_ret = torch.empty(n, dtype=torch.float32).pin_memory()
+    h_nt = torch.empty(n, dtype=torch.int32).pin_memory()
+    env.rollout_host_returns(h_act, h_ret, h_nt, chunk_steps=32)
+    assert torch.equal(env.xy, final)
+    assert torch.equal(h_nt.to(torch.int64), dense.terminated.sum(dim=0, dtype=torch.int64).cpu())
+    # return sums are accumulated per chunk launch in float32, in step order
+    acc = np.zeros(n, np.float32)
+    r = dense.reward.cpu().numpy()
+    for t in range(T):
+        acc = acc + r[t]
+    assert np.array_equal(h_ret.numpy(), acc)
