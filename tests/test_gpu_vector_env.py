@@ -140,9 +140,13 @@ def test_rollout_host_returns_matches_dense_rollout(golden):
     env.rollout_host_returns(h_act, h_ret, h_nt, chunk_steps=32)
     assert torch.equal(env.xy, final)
     assert torch.equal(h_nt.to(torch.int64), dense.terminated.sum(dim=0, dtype=torch.int64).cpu())
-    # return sums are accumulated per chunk launch in float32, in step order
+    # float32 return sums: each 32-step chunk launch sums its rewards in step order and adds the
+    # partial sum to the running total
     acc = np.zeros(n, np.float32)
     r = dense.reward.cpu().numpy()
-    for t in range(T):
-        acc = acc + r[t]
+    for lo in range(0, T, 32):
+        part = np.zeros(n, np.float32)
+        for t in range(lo, min(T, lo + 32)):
+            part = part + r[t]
+        acc = acc + part
     assert np.array_equal(h_ret.numpy(), acc)
