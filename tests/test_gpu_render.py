@@ -149,3 +149,49 @@ def test_render_argument_errors(setup):
         engine.render(xy, 0, pad_cells=(2, 2))
     with pytest.raises(ValueError):
         engine.render(xy, 0, dtype="float16")
+
+
+def test_render_fuzz_alignment_paths(golden):
+    """Random small puzzles, odd pixels_per_cell / border widths / paddings and batches whose frames
+    start at odd byte offsets: exercises the 16-byte, 4-byte and byte-wise row copies and the
+    persistent-CTA frame loop; every frame must equal the oracle's padded observation."""
+    from pushworld_b200.engine import Engine
+
+    rng = np.random.default_rng(404)
+    texts = []
+    while len(texts) < 6:
+        w, h = int(rng.integers(2, 7)), int(rng.integers(2, 6))
+        grid = [["." for _ in range(w)] for _ in range(h)]
+        for name in ["a", "m0", "g0", "m1", "m1", "w", "aw", "m2", "m2"]:
+            x, y = int(rng.integers(w)), int(rng.integers(h))
+            if grid[y][x] == ".":
+                grid[y][x] = name
+        text = "\n".join(" ".join(r) for r in grid) + "\n"
+        try:
+            po.OraclePuzzle(text)
+            texts.append(text)
+        except (ValueError, AssertionError):
+            pass
+    engine = Engine(texts)
+    oracles = [po.OraclePuzzle(t) for t in texts]
+    n = 37
+    pids = rng.integers(0, len(texts), size=n)
+    states = []
+    for p in pids:
+        s = oracles[p].initial_state
+        for _ in range(int(rng.integers(0, 12))):
+            s = oracles[p].get_next_state(s, int(rng.integers(4)))
+        states.append(s)
+    xy = engine.state_from_tuples(states)
+    puzzle_id = torch.tensor(pids, dtype=torch.int32, device="cuda")
+    for ppc, bw, extra in ((3, 1, (0, 0)), (5, 2, (1, 0)), (7, 1, (0, 1)), (4, 1, (2, 3)), (9, 4, (1, 1))):
+        pad = (engine.max_height + extra[0], engine.max_width + extra[1])
+        for dtype in ("uint8", "float32"):
+            got = engine.render(xy, puzzle_id, dtype=dtype, pixels_per_cell=ppc, border_width=bw,
+                                pad_cells=pad).cpu().numpy()
+            for e in range(n):
+                want = po.render_observation_padded(oracles[pids[e]], states[e], pad[0], pad[1], ppc, bw)
+                if dtype == "uint8":
+                    assert np.array_equal(got[e].astype(np.float32) / 255, want), (ppc, bw, e)
+                else:
+                    assert np.array_equal(got[e], want), (ppc, bw, e)
