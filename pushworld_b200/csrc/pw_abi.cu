@@ -359,6 +359,10 @@ int pw_rollout(PwEngine* e, int64_t n_envs, int32_t n_steps, const int32_t* puzz
   p.uniform_u64 = puzzle_id ? 0 : e->puzzles[(size_t)puzzle_uniform].size_u64;
   p.n_max = e->n_max;
   p.board_bits = puzzle_id ? e->board_bits_all : e->board_bits[(size_t)puzzle_uniform];
+  if (!puzzle_id) {
+    const PuzzleInfo& info = e->puzzles[(size_t)puzzle_uniform];
+    if (p.board_bits <= 32 && ring_fits(p.board_bits, info.width - 1)) p.ring_goals = info.g;
+  }
   p.board_static = puzzle_id ? e->d_board_static : e->d_board_static + puzzle_uniform;
   p.x = x;
   p.y = y;

@@ -236,6 +236,92 @@ PW_HD uint32_t board_step(Board<NMAX, Word>& s, int action, const BoardAction<Wo
   return pushed;
 }
 
+// ---- ring boards: uint32 boards with P spare bits -----------------------------------------
+// When bits + P <= 32 the unused top of the word becomes one GUARD ZONE [bits, 32) that is set in
+// both wall boards, and a move is a single ROTATE:
+//   * RIGHT / DOWN rotate left by 1 / P: nothing wraps (the highest cell bit is bits - 1, and
+//     bits - 1 + P <= 31); a cell leaving the last interior row lands in the guard zone.
+//   * LEFT / UP rotate left by 31 / 32 - P: objects never own bit 0 or a guard column, so the only
+//     bits that wrap are the cells of the first interior row moving UP (bits 1 .. P-1), and they
+//     land on 33 - P .. 31 >= bits: again the guard zone.
+// The guard zone therefore replaces the edge-row tests of board_step, and a regular state stays
+// free of guard bits because a move that puts any bit there is blocked.  One SHF per object and
+// one AND per wall test instead of two and two.
+PW_HD uint32_t rotl32(uint32_t v, uint32_t s) {
+#if defined(__CUDA_ARCH__)
+  return __funnelshift_l(v, v, s);  // wraps: uses s & 31
+#else
+  s &= 31u;
+  return s ? (v << s) | (v >> (32u - s)) : v;
+#endif
+}
+
+PW_HD bool ring_fits(int bits, int P) { return bits + P <= 32; }
+PW_HD uint32_t ring_guard(int bits) { return ~((1u << bits) - 1u); }
+// rotate-left amount of action a in byte a (puzzle.py:43-50: LEFT, RIGHT, UP, DOWN)
+PW_HD uint32_t ring_amounts(int P) {
+  return 31u | (1u << 8) | ((32u - (uint32_t)P) << 16) | ((uint32_t)P << 24);
+}
+PW_HD uint32_t ring_amount_of(uint32_t amounts, uint32_t action) {
+#if defined(__CUDA_ARCH__)
+  uint32_t amount;  // raw prmt: no masking of the selector; bytes 1..3 are ignored by rotl32
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(amount) : "r"(amounts), "r"(0u), "r"(action));
+  return amount;
+#else
+  return (amounts >> (8u * (action & 3u))) & 0xffu;
+#endif
+}
+
+// One transition on ring boards; `wall` / `awall` include the guard zone, `valid` = action <= 3
+// (an invalid action is a no-op, like a blocked agent).  Returns the moved-object bitmask when
+// kMask, else 1 / 0 for moved / unchanged.  Same rule as board_step.
+template <int NMAX, bool kMask>
+PW_HD uint32_t ring_step(uint32_t (&b)[NMAX], const uint32_t wall, const uint32_t awall,
+                         const uint32_t amount, const bool valid) {
+  uint32_t m[NMAX];
+#pragma unroll
+  for (int k = 0; k < NMAX; ++k) m[k] = rotl32(b[k], amount);
+  bool blocked = !valid | ((m[0] & awall) != 0);  // puzzle.py:353-354
+  if (NMAX <= 3) {
+    bool p1 = false, p2 = false;
+    if (NMAX == 2) {
+      p1 = (m[0] & b[1]) != 0;
+    } else if (NMAX == 3) {
+      // two pushable objects: direct pushes plus one level of chaining closes the set
+      const bool d1 = (m[0] & b[1]) != 0, d2 = (m[0] & b[NMAX - 1]) != 0;
+      p2 = d2 | (d1 & ((m[1] & b[NMAX - 1]) != 0));
+      p1 = d1 | (p2 & ((m[NMAX - 1] & b[1]) != 0));
+      blocked |= p2 & ((m[NMAX - 1] & wall) != 0);
+    }
+    if (NMAX >= 2) blocked |= p1 & ((m[1] & wall) != 0);  // transitive stopping, puzzle.py:376-379
+    const bool go = !blocked, go1 = go & p1, go2 = go & p2;
+    b[0] = go ? m[0] : b[0];
+    if (NMAX >= 2) b[1] = go1 ? m[1] : b[1];
+    if (NMAX == 3) b[NMAX - 1] = go2 ? m[NMAX - 1] : b[NMAX - 1];
+    if (kMask) return go ? (1u | (p1 ? 2u : 0u) | (p2 ? 4u : 0u)) : 0u;
+    return go ? 1u : 0u;
+  } else {
+    uint32_t u = m[0], hit = 0, pushed = 1u;
+    bool grow = !blocked;
+    while (grow) {
+      const uint32_t before = pushed;
+#pragma unroll
+      for (int j = 1; j < NMAX; ++j) {
+        if ((u & b[j]) != 0) {  // b[j] == 0 for j >= n
+          u |= m[j];
+          hit |= m[j] & wall;
+          pushed |= 1u << j;
+        }
+      }
+      grow = pushed != before;
+    }
+    pushed = (blocked | (hit != 0)) ? 0u : pushed;
+#pragma unroll
+    for (int k = 0; k < NMAX; ++k) b[k] = ((pushed >> k) & 1u) ? m[k] : b[k];
+    return kMask ? pushed : (pushed != 0 ? 1u : 0u);
+  }
+}
+
 template <int NMAX, typename Word>
 PW_HD int board_achieved(const Board<NMAX, Word>& s) {  // puzzle.py:396-407
   int count = 0;

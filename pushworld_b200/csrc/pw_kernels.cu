@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "pw_board.cuh"
 #include "pw_env.cuh"
 #include "pw_internal.h"
@@ -215,6 +217,171 @@ __global__ void __launch_bounds__(kBlock, MIN_BLOCKS)
     if (regular) {
       BoardSim<NMAX, Word> sim{s, st, 0u, 0};
       run_steps_sim<kLean>(sim, p, e, c);
+    } else {
+      general_slow_path(smem, p, e, c);
+    }
+  }
+  flush_counts(c, p, s_counters);
+}
+
+// ------------------------------------------------------------------------------------------
+// Ring-board rollout (pw_board.cuh: ring_step): the plain-rollout shape (reward + terminated per
+// step, nothing else) of a single puzzle whose board leaves P spare bits in a uint32.  The loop
+// is written out here instead of going through run_steps_sim because every instruction of it is
+// on the ALU pipe's critical path: one rotate per object, predicate-only push logic, running
+// output pointers, and (kG1: one goal object, the common case) reward and terminated decided by
+// a single compare.
+// ------------------------------------------------------------------------------------------
+template <int NMAX, bool kG1>
+__device__ __forceinline__ void run_ring_lean(const Board<NMAX, uint32_t>& s, const StepParams& p,
+                                              const int64_t e, const float* s_r4, StepCounts& c) {
+  uint32_t b[NMAX];
+#pragma unroll
+  for (int k = 0; k < NMAX; ++k) b[k] = s.b[k];
+  const uint32_t guard = ring_guard(p.board_bits);
+  const uint32_t wall = s.wall | guard, awall = s.awall | guard;
+  const uint32_t amounts = ring_amounts(s.P);
+  const int g = s.g;
+  // one-goal flag arithmetic below needs (board XOR goal) < 2^22: an unreachable goal (all ones)
+  // becomes the guard bit 0, which no object ever owns
+  const uint32_t goal0 = s.goal[0] == 0xffffffffu ? 1u : s.goal[0];
+  const size_t N = (size_t)p.N;
+  const int T = p.T;
+  const uint8_t* __restrict__ pa = p.actions + e;
+  float* __restrict__ pr = p.reward + e;
+  uint8_t* __restrict__ pt = p.terminated + e;
+  auto achieved = [&]() -> int {
+    int count = 0;
+#pragma unroll
+    for (int k = 0; k + 1 < NMAX; ++k) count += (b[k + 1] == s.goal[k]) ? 1 : 0;  // goal[k >= g] never matches
+    return count;
+  };
+  int prev = achieved();
+  // kG1: on4 = 4 * (the goal object sat on its goal after the previous step); the reward is
+  // s_r4[2 * terminated + previously_on_goal], read with the byte offset 8 * terminated + on4.
+  // Everything derived from `terminated` below is a multiply-add, i.e. off the ALU pipe.
+  uint32_t on4 = (kG1 && b[1] == goal0) ? 4u : 0u;
+  uint32_t n_term = 0, n_both4 = 0, n_moved = 0, n_gain = 0, n_invalid = 0;
+  auto one_step = [&](const uint32_t a, auto checked) {
+    constexpr bool kChecked = decltype(checked)::value;
+    const bool valid = kChecked ? a <= 3u : true;
+    n_moved += ring_step<NMAX, false>(b, wall, awall, ring_amount_of(amounts, a), valid);
+    uint32_t tbyte;
+    float r;
+    if (kG1) {
+      // puzzle.py:409-411 with one goal object, as a multiply-add: d = board XOR goal < 2^22, so
+      // the high word of d * -1000 is -1 for d != 0 and 0 for d == 0.  (A compare would make the
+      // flag a predicate and everything derived from it below a select on the ALU pipe.)
+      asm("mad.hi.s32 %0, %1, -1000, 1;" : "=r"(tbyte) : "r"(b[1] ^ goal0));
+      r = *reinterpret_cast<const float*>(reinterpret_cast<const char*>(s_r4) + (tbyte * 8u + on4));
+      n_both4 += tbyte * on4;
+      on4 = tbyte * 4u;
+    } else {
+      const int ach = achieved();
+      const bool term = ach == g;
+      const int dg = ach - prev;
+      prev = ach;
+      // gym_env.py:212-221; the float64 value (dg - 0.01) was rounded to float32 once, on the host
+      r = term ? 10.0f : c_reward_lut[dg + kMaxObjects];
+      n_gain += (uint32_t)max(dg, 0);
+      tbyte = term ? 1u : 0u;
+    }
+    n_term += tbyte;
+    if (kChecked) n_invalid += valid ? 0u : 1u;
+    *pr = r;
+    *pt = (uint8_t)tbyte;
+    pr += N;
+    pt += N;
+  };
+  // Actions do not depend on the state: the 4 loads of the next group are issued before the
+  // current group's steps run.  Two register buffers alternate (no copies), so a loaded action
+  // is first touched a full group later, by the step that uses it.  A group whose 4 actions are
+  // all valid (one test on their OR) runs without per-step action checks.
+  constexpr int kGroup = 4;
+  const int groups = T / kGroup;
+  const size_t group_stride = (size_t)kGroup * N;
+  auto load_group = [&](uint32_t (&buf)[kGroup]) {
+#pragma unroll
+    for (int k = 0; k < kGroup; ++k) buf[k] = pa[(size_t)k * N];
+  };
+  auto run_group = [&](const uint32_t (&buf)[kGroup]) {
+    if ((buf[0] | buf[1] | buf[2] | buf[3]) <= 3u) {
+#pragma unroll
+      for (int k = 0; k < kGroup; ++k) one_step(buf[k], std::false_type{});
+    } else {
+      uint32_t packed = buf[0] | (buf[1] << 8) | (buf[2] << 16) | (buf[3] << 24);
+#pragma unroll 1
+      for (int k = 0; k < kGroup; ++k, packed >>= 8) one_step(packed & 0xffu, std::true_type{});
+    }
+  };
+  uint32_t buf_a[kGroup], buf_b[kGroup];
+  if (groups > 0) load_group(buf_a);
+  for (int gi = 0; gi < groups; gi += 2) {
+    // the group after the last one re-reads the last one (never used): no predicated loads
+    pa += gi + 1 < groups ? group_stride : 0;
+    load_group(buf_b);
+    run_group(buf_a);
+    if (gi + 1 >= groups) break;
+    pa += gi + 2 < groups ? group_stride : 0;
+    load_group(buf_a);
+    run_group(buf_b);
+  }
+  int t = groups * kGroup;
+#pragma unroll 1
+  for (; t < T; ++t) one_step(p.actions[(size_t)t * N + e], std::true_type{});
+  c.terminated += n_term;
+  c.moved += n_moved;
+  c.dgoals += kG1 ? n_term - (n_both4 >> 2) : n_gain;  // gained = on the goal now and not before
+  c.invalid += n_invalid;
+  // positions back from the boards
+#pragma unroll
+  for (int k = 0; k < NMAX; ++k)
+    if (k < s.n) {
+      int x, y;
+      board_position<uint32_t>(b[k], s.P, &x, &y);
+      p.x[k * p.stride + e] = x;
+      p.y[k * p.stride + e] = y;
+    }
+}
+
+template <int NMAX, bool kG1, int MIN_BLOCKS>
+__global__ void __launch_bounds__(kBlock, MIN_BLOCKS)
+    k_rollout_ring(const __grid_constant__ StepParams p) {
+  extern __shared__ uint64_t smem[];
+  __shared__ uint32_t s_counters[4];
+  __shared__ BoardStatic<uint32_t> st;
+  __shared__ float s_r4[4];  // gym_env.py:212-221 for one goal object: -0.01, -1.01, 10, 10
+  if (threadIdx.x < 4) {
+    s_counters[threadIdx.x] = 0;
+    s_r4[threadIdx.x] = threadIdx.x >= 2 ? 10.0f : c_reward_lut[kMaxObjects - (int)threadIdx.x];
+  }
+  const SharedTable tbl{smem};
+  const BoardStaticPod* __restrict__ pod = p.board_static;
+  if (threadIdx.x < 8) st.goal[threadIdx.x] = (uint32_t)__ldg(&pod->goal[threadIdx.x]);
+  if (threadIdx.x == 0) {
+    st.wall = (uint32_t)__ldg(&pod->wall);
+    st.awall = (uint32_t)__ldg(&pod->awall);
+    st.P = __ldg(&pod->P);
+    st.n = __ldg(&pod->n);
+    st.g = __ldg(&pod->g);
+  }
+  stage_table(smem, p.blob + p.puzzle_off[p.puzzle_uniform], p.uniform_u64);  // ends with a barrier
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  StepCounts c;
+  if (e < p.N) {
+    Board<NMAX, uint32_t> s;
+    s.wall = st.wall;
+    s.awall = st.awall;
+    s.edge_up = s.edge_down = 0;
+    s.P = st.P;
+    s.n = st.n;
+    s.g = st.g;
+#pragma unroll
+    for (int k = 0; k < NMAX; ++k) s.goal[k] = st.goal[k];
+    const bool regular = board_load(s, tbl, [&](int k) { return p.x[k * p.stride + e]; },
+                                    [&](int k) { return p.y[k * p.stride + e]; });
+    if (regular) {
+      run_ring_lean<NMAX, kG1>(s, p, e, s_r4, c);
     } else {
       general_slow_path(smem, p, e, c);
     }
@@ -607,7 +774,25 @@ cudaError_t launch_steps(const StepParams& p, int n_limit, cudaStream_t stream) 
     else                                                                                        \
       k_steps_board<NB, uint64_t, MINB, true><<<grid, kBlock, tbl, stream>>>(p);                \
   } while (0)
-      if (lean) {
+      if (lean && p.ring_goals > 0 && n_limit >= 2) {
+        // ring boards: one rotate per object, guard zone instead of edge rows
+#define PW_RING(NB, MINB)                                                                       \
+  do {                                                                                          \
+    if (p.ring_goals == 1)                                                                      \
+      k_rollout_ring<NB, true, MINB><<<grid, kBlock, tbl, stream>>>(p);                         \
+    else                                                                                        \
+      k_rollout_ring<NB, false, MINB><<<grid, kBlock, tbl, stream>>>(p);                        \
+  } while (0)
+        switch (n_limit) {
+          case 2: PW_RING(2, 8); break;
+          case 3: PW_RING(3, 8); break;
+          case 4: PW_RING(4, 8); break;
+          case 5:
+          case 6: PW_RING(6, 8); break;
+          default: PW_RING(8, 6); break;
+        }
+#undef PW_RING
+      } else if (lean) {
         switch (n_limit) {
           case 1:
           case 2: PW_BOARD(2, 8); break;

@@ -100,6 +100,41 @@ static int board_walk(const uint64_t* blob, int* x, int* y, const uint8_t* actio
   return board_walk_n<Word, 8>(blob, x, y, actions, n_actions, xs, ys, moved, achieved);
 }
 
+// ring boards (pw_board.cuh: one rotate per object, guard zone instead of edge rows)
+template <int NMAX>
+static int ring_walk_n(const uint64_t* blob, int* x, int* y, const uint8_t* actions, int n_actions,
+                       int* xs, int* ys, uint32_t* moved, int* achieved) {
+  HostTable t{blob};
+  const int W = t.word(pw::kHdrDims) & 0xffff, H = t.word(pw::kHdrDims) >> 16;
+  const int n = t.word(pw::kHdrCounts) & 0xffff;
+  const int bits = pw::board_bits(W, H);
+  if (!pw::ring_fits(bits, W - 1) || n > NMAX) return -1;
+  pw::Board<NMAX, uint32_t> s;
+  pw::board_init(s, t);
+  if (!pw::board_load(s, t, [&](int k) { return x[k]; }, [&](int k) { return y[k]; })) return -2;
+  const uint32_t guard = pw::ring_guard(bits), amounts = pw::ring_amounts(s.P);
+  uint32_t b[NMAX];
+  for (int k = 0; k < NMAX; ++k) b[k] = s.b[k];
+  for (int i = 0; i < n_actions; ++i) {
+    const uint32_t a = actions[i];
+    moved[i] = pw::ring_step<NMAX, true>(b, s.wall | guard, s.awall | guard,
+                                         pw::ring_amount_of(amounts, a), a <= 3u);
+    for (int k = 0; k < NMAX; ++k) s.b[k] = b[k];
+    achieved[i] = pw::board_achieved(s);
+    for (int k = 0; k < n; ++k)
+      pw::board_position<uint32_t>(b[k], s.P, &xs[(size_t)i * n + k], &ys[(size_t)i * n + k]);
+  }
+  return n;
+}
+
+static int ring_walk(const uint64_t* blob, int* x, int* y, const uint8_t* actions, int n_actions,
+                     int* xs, int* ys, uint32_t* moved, int* achieved) {
+  const int n = reinterpret_cast<const uint32_t*>(blob)[pw::kHdrCounts] & 0xffff;
+  if (n <= 2) return ring_walk_n<2>(blob, x, y, actions, n_actions, xs, ys, moved, achieved);
+  if (n == 3) return ring_walk_n<3>(blob, x, y, actions, n_actions, xs, ys, moved, achieved);
+  return ring_walk_n<8>(blob, x, y, actions, n_actions, xs, ys, moved, achieved);
+}
+
 extern "C" {
 
 // Same walk through the compact bitboard rule (pw_board.cuh, NMAX = 8).  word_bits selects
@@ -107,6 +142,8 @@ extern "C" {
 // regular.
 int hc_board_walk(const uint64_t* blob, int word_bits, int* x, int* y, const uint8_t* actions,
                   int n_actions, int* xs, int* ys, uint32_t* moved, int* achieved) {
+  if (word_bits == 31)  // ring boards
+    return ring_walk(blob, x, y, actions, n_actions, xs, ys, moved, achieved);
   if (word_bits == 32)
     return board_walk<uint32_t>(blob, x, y, actions, n_actions, xs, ys, moved, achieved);
   return board_walk<uint64_t>(blob, x, y, actions, n_actions, xs, ys, moved, achieved);

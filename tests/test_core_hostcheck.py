@@ -64,7 +64,7 @@ def test_cell_code_matches_reference_renders(golden):
 def test_bitboard_rule_matches_reference_vectors(golden):
     """pw_board.cuh (whole-grid uint64 boards, used when width*height <= 64) on every golden
     transition of every eligible puzzle, and against the general rule on random walks."""
-    eligible = n32 = 0
+    eligible = n32 = nring = 0
     for key in golden.keys():
         rec = golden.rec(key)
         bits = 1 + (rec["height"] - 2) * (rec["width"] - 1)
@@ -82,6 +82,9 @@ def test_bitboard_rule_matches_reference_vectors(golden):
             if bits <= 32:
                 outs.append(hostcheck.board_walk(blob, parsed.initial_state, actions, 32))
                 n32 += 1
+            if bits + rec["width"] - 1 <= 32:  # ring boards (word_bits 31 selects them)
+                outs.append(hostcheck.board_walk(blob, parsed.initial_state, actions, 31))
+                nring += 1
             if outs[0] is None:
                 assert not regular, key
                 continue
@@ -94,14 +97,14 @@ def test_bitboard_rule_matches_reference_vectors(golden):
             mbits = (moved[:, None] >> np.arange(ref.shape[1])[None, :]) & 1
             assert np.array_equal(mbits.astype(bool), changed), key
         eligible += 1
-    assert eligible >= 10 and n32 >= 5, (eligible, n32)
+    assert eligible >= 10 and n32 >= 5 and nring >= 2, (eligible, n32, nring)
 
 
 def test_bitboard_rule_equals_general_rule_on_random_small_puzzles():
     """Random small puzzles (multi-cell shapes, chains, agent walls): bitboard == general rule,
     including invalid actions."""
     rng = np.random.default_rng(2026)
-    checked = 0
+    checked = ring_checked = 0
     for trial in range(300):
         w, h = int(rng.integers(3, 7)), int(rng.integers(2, 7))
         bits = 1 + h * (w + 1)
@@ -126,8 +129,8 @@ def test_bitboard_rule_equals_general_rule_on_random_small_puzzles():
         blob = tables.build_blob(parsed)
         actions = rng.integers(0, 5, size=200).astype(np.uint8)  # 4 = invalid -> no-op
         ref = hostcheck.walk(blob, parsed.initial_state, actions)
-        for word_bits in (32, 64):
-            if bits > word_bits:
+        for word_bits in (31, 32, 64):
+            if bits + (w + 1 if word_bits == 31 else 0) > max(word_bits, 32):
                 continue
             out = hostcheck.board_walk(blob, parsed.initial_state, actions, word_bits)
             if out is None:
@@ -135,7 +138,8 @@ def test_bitboard_rule_equals_general_rule_on_random_small_puzzles():
             for got, want in zip(out, ref):
                 assert np.array_equal(got, want), text
             checked += 1
-    assert checked > 100
+            ring_checked += word_bits == 31
+    assert checked > 100 and ring_checked > 30, (checked, ring_checked)
 
 
 def test_general_rule_matches_oracle_on_irregular_puzzles():

@@ -441,3 +441,89 @@ def test_mixed_bitboard_kernel_matches_oracle_and_handles_irregular_inputs(golde
         got = tuple((int(final[0, j, e]), int(final[1, j, e])) for j in range(o.num_objects))
         assert got == st, e
     assert engine.poll_invalid_actions() == int((actions > 3).sum()) + int((actions[0] > 3).sum())
+
+
+def _random_small_puzzle(rng, max_bits_plus_pitch=32):
+    """A random regular puzzle whose board leaves a spare pitch in a uint32 (ring-board eligible)."""
+    while True:
+        w, h = int(rng.integers(2, 7)), int(rng.integers(1, 6))
+        if 1 + h * (w + 1) + (w + 1) > max_bits_plus_pitch:
+            continue
+        grid = [["." for _ in range(w)] for _ in range(h)]
+        n_mov = int(rng.integers(1, 8))
+        names = ["a"] + [f"m{k}" for k in range(n_mov)]
+        for name in names:
+            for _ in range(int(rng.integers(1, 3))):
+                x, y = int(rng.integers(w)), int(rng.integers(h))
+                if grid[y][x] == ".":
+                    grid[y][x] = name
+        extras = ["w", "aw"] + [f"g{k}" for k in range(int(rng.integers(1, min(n_mov, 3) + 1)))]
+        for name in extras:
+            x, y = int(rng.integers(w)), int(rng.integers(h))
+            if grid[y][x] == ".":
+                grid[y][x] = name
+        text = "\n".join(" ".join(row) for row in grid) + "\n"
+        try:
+            oracle = po.OraclePuzzle(text)
+        except (ValueError, AssertionError):
+            continue
+        if oracle.num_objects < 2 or len(oracle.goal_state) < 1:
+            continue
+        return text, oracle
+
+
+def test_ring_rollout_kernel_matches_oracle(golden):
+    """The ring-board rollout kernel (k_rollout_ring: plain rollouts of a single puzzle whose board
+    leaves one spare pitch in a uint32): reward, terminated, final state and the counters against
+    the oracle for benchmark puzzles and random small puzzles (2..8 objects, 1..3 goals), with
+    invalid actions, step counts around the 4-step group size and irregular start states."""
+    from pushworld_b200.engine import Engine
+
+    rng = np.random.default_rng(4242)
+    cases = [(golden.text(k), po.OraclePuzzle(golden.text(k)))
+             for k in ("benchmark/level1/Road Block", "benchmark/level1/Obstacle Has Obstacle")]
+    cases += [_random_small_puzzle(rng) for _ in range(40)]
+    seen_n, seen_g = set(), set()
+    for ci, (text, oracle) in enumerate(cases):
+        assert 1 + (oracle.height - 2) * (oracle.width - 1) + oracle.width - 1 <= 32
+        engine = Engine([text])
+        seen_n.add(oracle.num_objects)
+        seen_g.add(len(oracle.goal_state))
+        n = 96
+        states = []
+        for e in range(n):
+            st = oracle.initial_state
+            for _ in range(int(rng.integers(0, 25))):
+                st = oracle.get_next_state(st, int(rng.integers(4)))
+            if e % 11 == 5 and oracle.num_objects >= 3:  # irregular: object 2 dropped onto object 1
+                st = st[:2] + (st[1],) + st[3:]
+            states.append(st)
+        for T in ([1, 3, 4, 5, 8, 41] if ci < 4 else [int(rng.integers(1, 60))]):
+            hi = 4 if ci % 3 else 6  # some cases with invalid actions (4, 5)
+            actions = rng.integers(0, hi, size=(T, n)).astype(np.uint8)
+            if ci % 5 == 0:
+                actions[rng.integers(0, T), rng.integers(0, n)] = 255
+            xy = engine.state_from_tuples(states)
+            reward = torch.empty((T, n), dtype=torch.float32, device="cuda")
+            term = torch.empty((T, n), dtype=torch.uint8, device="cuda")
+            counters = torch.zeros(4, dtype=torch.int64, device="cuda")
+            engine.rollout(xy, 0, torch.from_numpy(actions).cuda(), reward=reward, terminated=term,
+                           counters=counters)
+            final, r, te = xy.cpu().numpy(), reward.cpu().numpy(), term.cpu().numpy()
+            n_term = n_moved = n_gain = 0
+            for e in range(n):
+                st = states[e]
+                for t in range(T):
+                    a = int(actions[t, e])
+                    nxt = st if a > 3 else oracle.get_next_state(st, a)
+                    rr, tt, _ = po.step_reward(oracle, st, nxt)
+                    assert np.float32(rr) == r[t, e] and tt == bool(te[t, e]), (text, T, e, t)
+                    n_term += tt
+                    n_moved += nxt != st
+                    n_gain += max(oracle.count_achieved_goals(nxt) - oracle.count_achieved_goals(st), 0)
+                    st = nxt
+                got = tuple((int(final[0, j, e]), int(final[1, j, e])) for j in range(oracle.num_objects))
+                assert got == st, (text, T, e)
+            assert counters.cpu().numpy().tolist() == [n * T, n_term, n_moved, n_gain], (text, T)
+            assert engine.poll_invalid_actions() == int((actions > 3).sum())
+    assert len(seen_n) >= 5 and len(seen_g) >= 2, (seen_n, seen_g)
