@@ -234,7 +234,8 @@ __global__ void __launch_bounds__(kBlock, MIN_BLOCKS)
 // ------------------------------------------------------------------------------------------
 template <int NMAX, bool kG1>
 __device__ __forceinline__ void run_ring_lean(const Board<NMAX, uint32_t>& s, const StepParams& p,
-                                              const int64_t e, const float* s_r4, StepCounts& c) {
+                                              const int64_t e, const float* s_r4, uint8_t* tiles,
+                                              StepCounts& c) {
   uint32_t b[NMAX];
 #pragma unroll
   for (int k = 0; k < NMAX; ++k) b[k] = s.b[k];
@@ -245,11 +246,19 @@ __device__ __forceinline__ void run_ring_lean(const Board<NMAX, uint32_t>& s, co
   // one-goal flag arithmetic below needs (board XOR goal) < 2^22: an unreachable goal (all ones)
   // becomes the guard bit 0, which no object ever owns
   const uint32_t goal0 = s.goal[0] == 0xffffffffu ? 1u : s.goal[0];
-  const size_t N = (size_t)p.N;
   const int T = p.T;
-  const uint8_t* __restrict__ pa = p.actions + e;
-  float* __restrict__ pr = p.reward + e;
-  uint8_t* __restrict__ pt = p.terminated + e;
+  // Addressing.  A lean launch has T * N < 2^32 and the ring launcher requires N even, so the
+  // element offset of (t, e) is 2 * h + (e & 1) with the 32-bit h = (e >> 1) + t * (N / 2):
+  // every address is one IMAD.WIDE (h times 2 or 8 bytes, plus a per-thread base) on the FMA pipe.
+  // (A multiplier of 1 would be strength-reduced to an add-with-carry pair on the ALU pipe.)
+  const uint32_t half_n = (uint32_t)(p.N >> 1);
+  uint8_t* term_base = p.terminated + (e & 1);
+  float* const reward_base = p.reward + (e & 1);
+  // keep the byte base an opaque per-thread register pair: otherwise the compiler splits it back
+  // into (uniform pointer) + (offset) and adds the pointer with a carry pair per access
+  // (and a PTX store below, because the opaque base has lost its address space)
+  asm volatile("" : "+l"(term_base));
+  uint32_t h_out = (uint32_t)(e >> 1);  // half offset of the step being written
   auto achieved = [&]() -> int {
     int count = 0;
 #pragma unroll
@@ -288,47 +297,55 @@ __device__ __forceinline__ void run_ring_lean(const Board<NMAX, uint32_t>& s, co
     }
     n_term += tbyte;
     if (kChecked) n_invalid += valid ? 0u : 1u;
-    *pr = r;
-    *pt = (uint8_t)tbyte;
-    pr += N;
-    pt += N;
+    reward_base[(size_t)h_out * 2u] = r;
+    asm volatile("st.global.u8 [%0], %1;" ::"l"(term_base + (size_t)h_out * 2u), "r"(tbyte) : "memory");
+    h_out += half_n;
   };
-  // Actions do not depend on the state: the 4 loads of the next group are issued before the
-  // current group's steps run.  Two register buffers alternate (no copies), so a loaded action
-  // is first touched a full group later, by the step that uses it.  A group whose 4 actions are
-  // all valid (one test on their OR) runs without per-step action checks.
-  constexpr int kGroup = 4;
-  const int groups = T / kGroup;
-  const size_t group_stride = (size_t)kGroup * N;
-  auto load_group = [&](uint32_t (&buf)[kGroup]) {
-#pragma unroll
-    for (int k = 0; k < kGroup; ++k) buf[k] = pa[(size_t)k * N];
+  // Actions do not depend on the state, so they are staged a whole block of 32 steps ahead:
+  // lane l copies the 32 action bytes of the warp's environments for step 32 * block + l
+  // (one 32-byte sector of actions[T][N]) straight into shared memory with cp.async, into one of
+  // two [32 steps][32 envs] tiles per warp.  A step then reads its action with one LDS at an
+  // immediate offset: no address arithmetic, no registers held across the DRAM latency.
+  // Each lane also tests the row it copied for invalid actions; the warp votes, and a block
+  // without any runs with no per-step action checks.
+  constexpr int kBlockSteps = 32, kGroup = 4;
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint8_t* const warp_actions = p.actions + (e - (int64_t)lane);
+  const uint32_t tiles_s = (uint32_t)__cvta_generic_to_shared(tiles);
+  auto issue_block = [&](const int block) {
+    const int row = block * kBlockSteps + (int)lane;
+    const uint8_t* src = warp_actions + (size_t)(row < T ? row : T - 1) * (size_t)p.N;  // clamped: never used
+    const uint32_t dst = tiles_s + (uint32_t)(block & 1) * 1024u + lane * 32u;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u), "l"(src + 16) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
   };
-  auto run_group = [&](const uint32_t (&buf)[kGroup]) {
-    if ((buf[0] | buf[1] | buf[2] | buf[3]) <= 3u) {
+  const int blocks = (T + kBlockSteps - 1) / kBlockSteps;
+  issue_block(0);
+  for (int blk = 0; blk < blocks; ++blk) {
+    __syncwarp();          // every lane is done with the tile the next block lands in
+    issue_block(blk + 1);  // past the end: re-reads the last row, never used
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+    __syncwarp();  // block `blk` is visible to the whole warp
+    const uint8_t* tile = tiles + (blk & 1) * 1024;
+    const uint4 w0 = *reinterpret_cast<const uint4*>(tile + lane * 32u);
+    const uint4 w1 = *reinterpret_cast<const uint4*>(tile + lane * 32u + 16u);
+    const uint32_t seen = w0.x | w0.y | w0.z | w0.w | w1.x | w1.y | w1.z | w1.w;
+    const bool any_invalid = __any_sync(0xffffffffu, (seen & 0xfcfcfcfcu) != 0u);
+    const int steps = T - blk * kBlockSteps < kBlockSteps ? T - blk * kBlockSteps : kBlockSteps;
+    const uint8_t* mine = tile + lane;
+    if (!any_invalid && steps == kBlockSteps) {
+#pragma unroll 1
+      for (int gi = 0; gi < kBlockSteps / kGroup; ++gi, mine += kGroup * 32) {
 #pragma unroll
-      for (int k = 0; k < kGroup; ++k) one_step(buf[k], std::false_type{});
+        for (int k = 0; k < kGroup; ++k) one_step(mine[k * 32], std::false_type{});
+      }
     } else {
-      uint32_t packed = buf[0] | (buf[1] << 8) | (buf[2] << 16) | (buf[3] << 24);
 #pragma unroll 1
-      for (int k = 0; k < kGroup; ++k, packed >>= 8) one_step(packed & 0xffu, std::true_type{});
+      for (int k = 0; k < steps; ++k, mine += 32) one_step(mine[0], std::true_type{});
     }
-  };
-  uint32_t buf_a[kGroup], buf_b[kGroup];
-  if (groups > 0) load_group(buf_a);
-  for (int gi = 0; gi < groups; gi += 2) {
-    // the group after the last one re-reads the last one (never used): no predicated loads
-    pa += gi + 1 < groups ? group_stride : 0;
-    load_group(buf_b);
-    run_group(buf_a);
-    if (gi + 1 >= groups) break;
-    pa += gi + 2 < groups ? group_stride : 0;
-    load_group(buf_a);
-    run_group(buf_b);
   }
-  int t = groups * kGroup;
-#pragma unroll 1
-  for (; t < T; ++t) one_step(p.actions[(size_t)t * N + e], std::true_type{});
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   c.terminated += n_term;
   c.moved += n_moved;
   c.dgoals += kG1 ? n_term - (n_both4 >> 2) : n_gain;  // gained = on the goal now and not before
@@ -351,6 +368,7 @@ __global__ void __launch_bounds__(kBlock, MIN_BLOCKS)
   __shared__ uint32_t s_counters[4];
   __shared__ BoardStatic<uint32_t> st;
   __shared__ float s_r4[4];  // gym_env.py:212-221 for one goal object: -0.01, -1.01, 10, 10
+  __shared__ __align__(16) uint8_t s_tiles[kBlock / 32][2][32 * 32];  // per warp: two action tiles
   if (threadIdx.x < 4) {
     s_counters[threadIdx.x] = 0;
     s_r4[threadIdx.x] = threadIdx.x >= 2 ? 10.0f : c_reward_lut[kMaxObjects - (int)threadIdx.x];
@@ -380,8 +398,10 @@ __global__ void __launch_bounds__(kBlock, MIN_BLOCKS)
     for (int k = 0; k < NMAX; ++k) s.goal[k] = st.goal[k];
     const bool regular = board_load(s, tbl, [&](int k) { return p.x[k * p.stride + e]; },
                                     [&](int k) { return p.y[k * p.stride + e]; });
-    if (regular) {
-      run_ring_lean<NMAX, kG1>(s, p, e, s_r4, c);
+    // The action tiles are filled by whole warps (the launcher guarantees N % 32 == 0, so a warp
+    // is full or empty): a warp with any irregular state takes the general rule for all its lanes.
+    if (__all_sync(0xffffffffu, regular)) {
+      run_ring_lean<NMAX, kG1>(s, p, e, s_r4, s_tiles[threadIdx.x >> 5][0], c);
     } else {
       general_slow_path(smem, p, e, c);
     }
@@ -774,7 +794,8 @@ cudaError_t launch_steps(const StepParams& p, int n_limit, cudaStream_t stream) 
     else                                                                                        \
       k_steps_board<NB, uint64_t, MINB, true><<<grid, kBlock, tbl, stream>>>(p);                \
   } while (0)
-      if (lean && p.ring_goals > 0 && n_limit >= 2) {
+      if (lean && p.ring_goals > 0 && n_limit >= 2 && (p.N & 31) == 0 &&
+          (reinterpret_cast<uintptr_t>(p.actions) & 15u) == 0) {
         // ring boards: one rotate per object, guard zone instead of edge rows
 #define PW_RING(NB, MINB)                                                                       \
   do {                                                                                          \
