@@ -350,7 +350,7 @@ def run_ours(args) -> None:
     achieved = units * fused_bpu / (kernel_ms * 1e-3) / 1e9
     roofline = {
         "bound": "hbm",
-        "kernel": "k_steps_board<3, uint32_t> (pw_rollout)",
+        "kernel": "k_rollout_ring<3, true> (pw_rollout)",
         "achieved": achieved,
         "peak": peak,
         "unit": "GB/s",
@@ -370,7 +370,10 @@ def run_ours(args) -> None:
     traffic_path = os.path.join(REPO, "profiles", "rollout_traffic.json")
     if os.path.exists(traffic_path):
         with open(traffic_path) as f:
-            roofline["traffic"] = json.load(f).get("dram_bytes_per_launch")
+            traffic = json.load(f)
+        roofline["traffic"] = traffic.get("dram_bytes_per_launch")
+        # secondary bound: the kernel is bound by the integer ALU pipe, not by HBM
+        roofline["secondary_bound"] = traffic.get("secondary_bound")
 
     cpu_rate, cpu_threads, cpu_sample = cpu_port_throughput(12.0)
     py_rate = python_port_throughput(3.0)
