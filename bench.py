@@ -218,7 +218,7 @@ def run_reference(args) -> None:
         "get_next_state; the Python reference cannot travel to the GPU box and its C++ twin "
         "needs Boost), OpenMP over all host threads",
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_RESULT_OUT, flush=True)
 
 
 # ---------------------------------------------------------------------------- our arm
@@ -419,7 +419,10 @@ def run_ours(args) -> None:
         "totals": {"env_steps": total_env_steps, "terminated_steps": int(totals[1].item()),
                    "moved_steps": int(totals[2].item()), "goals_gained": int(totals[3].item())},
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_RESULT_OUT, flush=True)
+
+
+_RESULT_OUT = sys.stdout
 
 
 def main() -> None:
@@ -429,6 +432,13 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     args = ap.parse_args()
+    # The contract is ONE JSON line on stdout.  Libraries may write banners to file descriptor 1
+    # (NCCL prints its version there when NCCL_DEBUG is set), so fd 1 is pointed at stderr for the
+    # whole run and the JSON line goes to a private duplicate of the original stdout.
+    global _RESULT_OUT
+    sys.stdout.flush()
+    _RESULT_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3  # timing rule: at least three warm-up steps
     if args.impl == "reference":
