@@ -498,7 +498,7 @@ def test_ring_rollout_kernel_matches_oracle(golden):
             if e % 11 == 5 and oracle.num_objects >= 3:  # irregular: object 2 dropped onto object 1
                 st = st[:2] + (st[1],) + st[3:]
             states.append(st)
-        for T in ([1, 3, 4, 5, 8, 41] if ci < 4 else [int(rng.integers(1, 60))]):
+        for T in ([1, 3, 4, 5, 8, 41, 64, 100, 131] if ci < 4 else [int(rng.integers(1, 60))]):
             hi = 4 if ci % 3 else 6  # some cases with invalid actions (4, 5)
             actions = rng.integers(0, hi, size=(T, n)).astype(np.uint8)
             if ci % 5 == 0:
