@@ -243,7 +243,7 @@ __device__ __forceinline__ void run_ring_lean(const Board<NMAX, uint32_t>& s, co
   const uint32_t wall = s.wall | guard, awall = s.awall | guard;
   const uint32_t amounts = ring_amounts(s.P);
   const int g = s.g;
-  // one-goal flag arithmetic below needs (board XOR goal) < 2^22: an unreachable goal (all ones)
+  // one-goal flag arithmetic below needs (board XOR goal) < 2^30: an unreachable goal (all ones)
   // becomes the guard bit 0, which no object ever owns
   const uint32_t goal0 = s.goal[0] == 0xffffffffu ? 1u : s.goal[0];
   const int T = p.T;
@@ -278,10 +278,11 @@ __device__ __forceinline__ void run_ring_lean(const Board<NMAX, uint32_t>& s, co
     uint32_t tbyte;
     float r;
     if (kG1) {
-      // puzzle.py:409-411 with one goal object, as a multiply-add: d = board XOR goal < 2^22, so
-      // the high word of d * -1000 is -1 for d != 0 and 0 for d == 0.  (A compare would make the
-      // flag a predicate and everything derived from it below a select on the ALU pipe.)
-      asm("mad.hi.s32 %0, %1, -1000, 1;" : "=r"(tbyte) : "r"(b[1] ^ goal0));
+      // puzzle.py:409-411 with one goal object, as a multiply-add: d = board XOR goal < 2^30 (ring
+      // boards have at most 30 bits), so the high word of d * -3 is -1 for d != 0 and 0 for d == 0.
+      // (A compare would make the flag a predicate and everything derived from it below a select
+      // on the ALU pipe; a multiplier of -1 would be strength-reduced to ALU instructions.)
+      asm("mad.hi.s32 %0, %1, -3, 1;" : "=r"(tbyte) : "r"(b[1] ^ goal0));
       r = *reinterpret_cast<const float*>(reinterpret_cast<const char*>(s_r4) + (tbyte * 8u + on4));
       n_both4 += tbyte * on4;
       on4 = tbyte * 4u;

@@ -446,7 +446,7 @@ def test_mixed_bitboard_kernel_matches_oracle_and_handles_irregular_inputs(golde
 def _random_small_puzzle(rng, max_bits_plus_pitch=32):
     """A random regular puzzle whose board leaves a spare pitch in a uint32 (ring-board eligible)."""
     while True:
-        w, h = int(rng.integers(2, 7)), int(rng.integers(1, 6))
+        w, h = int(rng.integers(1, 7)), int(rng.integers(1, 15))  # narrow and tall ones use the top bits
         if 1 + h * (w + 1) + (w + 1) > max_bits_plus_pitch:
             continue
         grid = [["." for _ in range(w)] for _ in range(h)]
@@ -482,10 +482,12 @@ def test_ring_rollout_kernel_matches_oracle(golden):
     rng = np.random.default_rng(4242)
     cases = [(golden.text(k), po.OraclePuzzle(golden.text(k)))
              for k in ("benchmark/level1/Road Block", "benchmark/level1/Obstacle Has Obstacle")]
-    cases += [_random_small_puzzle(rng) for _ in range(40)]
-    seen_n, seen_g = set(), set()
+    cases += [_random_small_puzzle(rng) for _ in range(60)]
+    seen_n, seen_g, max_bits = set(), set(), 0
     for ci, (text, oracle) in enumerate(cases):
         assert 1 + (oracle.height - 2) * (oracle.width - 1) + oracle.width - 1 <= 32
+        if len(oracle.goal_state) == 1:
+            max_bits = max(max_bits, 1 + (oracle.height - 2) * (oracle.width - 1))
         engine = Engine([text])
         seen_n.add(oracle.num_objects)
         seen_g.add(len(oracle.goal_state))
@@ -526,4 +528,4 @@ def test_ring_rollout_kernel_matches_oracle(golden):
                 assert got == st, (text, T, e)
             assert counters.cpu().numpy().tolist() == [n * T, n_term, n_moved, n_gain], (text, T)
             assert engine.poll_invalid_actions() == int((actions > 3).sum())
-    assert len(seen_n) >= 5 and len(seen_g) >= 2, (seen_n, seen_g)
+    assert len(seen_n) >= 5 and len(seen_g) >= 2 and max_bits >= 27, (seen_n, seen_g, max_bits)
