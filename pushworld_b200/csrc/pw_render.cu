@@ -1,7 +1,7 @@
-// pw_render.cu -- RGB observation kernel (optionally fused with one environment step).
+// pw_render.cu -- RGB observation kernel.  pw_step_render (BASELINE config 5) is the step launch of
+// pw_kernels.cu followed by this kernel on the same stream.
 //
-// One CTA per environment:
-//   0. (fused only) thread 0 performs the step on shared-memory state (BASELINE config 5);
+// One CTA renders a few environments, one after the other:
 //   1. every thread computes the 9-region colour code of some grid cells (pw_render_core.cuh)
 //      into shared memory -- W*H codes, 8 bytes each;
 //   2. per cell row, the block builds the 3 distinct pixel-row patterns (top border rows,
@@ -40,6 +40,7 @@ cudaError_t upload_palette(const uint8_t* rgb, const float* rgb_f32, int n_color
 namespace {
 
 constexpr int kRenderBlock = 256;
+constexpr int kBulkChunks = 4;  // 16-byte chunks per thread in the bulk cell-row emit (<= 16 KB per cell row)
 constexpr size_t kRenderMaxDynamicSmem = 227 * 1024 - 2048;
 
 struct SmemPos {
@@ -97,12 +98,11 @@ __device__ __forceinline__ void put_pixel<uint8_t>(uint8_t* dst, uint32_t pal, c
 
 // Persistent CTAs: CTA b owns environments b, b + G, b + 2G, ... (G = grid size), so that the CTAs
 // running at the same time write ADJACENT frames and the whole grid sweeps the output buffer
-// like one stream (contiguous chunks per CTA cost ~25 % of the HBM write bandwidth).  Fused mode
-// first steps all of the CTA's environments (one thread each), then the block renders them one
-// after the other; the puzzle table, the pixel-column map and the palette are staged once per
-// CTA and only re-staged when the puzzle changes.
-template <typename T, bool kFused>
-__global__ void __launch_bounds__(kRenderBlock) k_render(const RenderParams p, const StepParams sp) {
+// like one stream (contiguous chunks per CTA cost ~25 % of the HBM write bandwidth).  The puzzle
+// table, the pixel-column map and the palette are staged once per CTA and only re-staged when
+// the puzzle changes.
+template <typename T>
+__global__ void __launch_bounds__(kRenderBlock) k_render(const RenderParams p) {
   extern __shared__ __align__(16) uint64_t smem[];
   __shared__ float4 s_pal_f[16];
   __shared__ uint32_t s_pal_u[16];
@@ -131,22 +131,20 @@ __global__ void __launch_bounds__(kRenderBlock) k_render(const RenderParams p, c
   for (int i = threadIdx.x; i < (row_pitch >> 2); i += blockDim.x)
     reinterpret_cast<uint32_t*>(s_zero)[i] = 0u;
 
-  // ---- fused step of this CTA's environments (BASELINE config 5) ------------------------
-  if (kFused) {
-    uint32_t invalid = 0;
-    for (int64_t e = blockIdx.x + (int64_t)threadIdx.x * G; e < p.N; e += (int64_t)blockDim.x * G) {
-      const int pid = sp.puzzle_id ? sp.puzzle_id[e] : sp.puzzle_uniform;
-      LocalEnv<GlobalTable> env;
-      env.init(GlobalTable{sp.blob + sp.puzzle_off[pid]});
-      StepCounts counts;
-      run_steps_thread<false>(env, sp, e, counts);
-      invalid += counts.invalid;
-    }
-    if (invalid && sp.status) atomicAdd(&sp.status[0], (unsigned long long)invalid);
-  }
-  __syncthreads();  // new states (global memory) visible to the whole block
+  __syncthreads();
 
   const int ppc = p.ppc, bw = p.bw;
+  // bulk emit (see emit_cell_row_bulk): chunk c of a cell-row block lies in output row
+  // c * 16 / row_bytes; its source is that row's region pattern at the same column offset
+  const int bulk_chunks = (ppc * row_bytes) >> 4;
+  const bool use_bulk = (row_bytes & 15) == 0 && bulk_chunks <= kBulkChunks * kRenderBlock;
+  int bulk_src[kBulkChunks];
+#pragma unroll
+  for (int k = 0; k < kBulkChunks; ++k) {
+    const int byte = ((int)threadIdx.x + k * kRenderBlock) << 4;
+    const int oy = use_bulk ? byte / row_bytes : 0;
+    bulk_src[k] = region_of(oy < ppc ? oy : 0, ppc, bw) * row_pitch + (byte - oy * row_bytes);
+  }
   int cur_pid = -1, W = 0, H = 0, n = 0, img_h = 0, img_w = 0, pad_top = 0, pad_left = 0;
   for (int64_t e = blockIdx.x; e < p.N; e += G) {
     const int pid = p.puzzle_id ? p.puzzle_id[e] : p.puzzle_uniform;
@@ -201,12 +199,27 @@ __global__ void __launch_bounds__(kRenderBlock) k_render(const RenderParams p, c
     // builds the 3 region-row patterns of cell row cy into pattern set `buf`
     auto build = [&](int cy, int buf) {
       uint8_t* set = s_pat + buf * 3 * row_pitch;
-      for (int i = threadIdx.x; i < 3 * p.out_w; i += blockDim.x) {
-        const int rr = i / p.out_w, X = i - rr * p.out_w;
+      const uint64_t* codes = s_code + cy * W;
+      for (int X = threadIdx.x; X < p.out_w; X += blockDim.x) {
         const uint32_t m = s_xmap[X];
-        uint32_t pal = kPalPad;
-        if (m != 0xffffu) pal = (uint32_t)(s_code[cy * W + (m >> 2)] >> (4 * (rr * 3 + (m & 3u)))) & 15u;
-        put_pixel<T>(reinterpret_cast<T*>(set + rr * row_pitch) + 3 * X, pal, s_pal_f, s_pal_u);
+        const bool inside = m != 0xffffu;
+        const uint64_t code = inside ? codes[m >> 2] >> (4u * (m & 3u)) : 0ull;
+#pragma unroll
+        for (int rr = 0; rr < 3; ++rr) {
+          const uint32_t pal = inside ? (uint32_t)(code >> (12 * rr)) & 15u : kPalPad;
+          put_pixel<T>(reinterpret_cast<T*>(set + rr * row_pitch) + 3 * X, pal, s_pal_f, s_pal_u);
+        }
+      }
+    };
+    // Small rows (uint8 frames): the pixels_per_cell output rows of a cell row are one contiguous
+    // block of the frame, written here as 16-byte chunks with per-thread source offsets that were
+    // computed once per kernel (bulk_src), instead of one warp and ~40 instructions per row.
+    auto emit_cell_row_bulk = [&](int cy, const uint8_t* set) {
+      uint4* dst = reinterpret_cast<uint4*>(frame + (size_t)(pad_top + cy * ppc) * (size_t)row_bytes);
+#pragma unroll
+      for (int k = 0; k < kBulkChunks; ++k) {
+        const int c = (int)threadIdx.x + k * kRenderBlock;
+        if (c < bulk_chunks) dst[c] = *reinterpret_cast<const uint4*>(set + bulk_src[k]);
       }
     };
 
@@ -218,9 +231,13 @@ __global__ void __launch_bounds__(kRenderBlock) k_render(const RenderParams p, c
     for (int cy = 0; cy < H; ++cy) {
       if (cy + 1 < H) build(cy + 1, (cy + 1) & 1);  // next cell row while this one streams out
       const uint8_t* set = s_pat + (cy & 1) * 3 * row_pitch;
-      const int Y0 = pad_top + cy * ppc;
-      for (int oy = warp; oy < ppc; oy += n_warps)
-        emit(Y0 + oy, set + region_of(oy, ppc, bw) * row_pitch);
+      if (use_bulk && vec16) {
+        emit_cell_row_bulk(cy, set);
+      } else {
+        const int Y0 = pad_top + cy * ppc;
+        for (int oy = warp; oy < ppc; oy += n_warps)
+          emit(Y0 + oy, set + region_of(oy, ppc, bw) * row_pitch);
+      }
       __syncthreads();
     }
   }
@@ -230,15 +247,20 @@ __global__ void __launch_bounds__(kRenderBlock) k_render(const RenderParams p, c
 
 cudaError_t launch_render(const RenderParams& p, const StepParams* fused_step, int n_limit,
                           cudaStream_t stream) {
-  (void)n_limit;
   if (p.N == 0) return cudaSuccess;
   const int elem = p.dtype == 1 ? 4 : 1;
   const size_t row_pitch = ((size_t)p.out_w * 3 * elem + 15) & ~(size_t)15;
   const size_t smem = (size_t)p.max_blob_u64 * 8 + (size_t)p.max_cells * 8 + 64 * sizeof(int) +
                       (size_t)p.out_w * 2 + 16 + 7 * row_pitch;
   if (smem > kRenderMaxDynamicSmem) return cudaErrorInvalidValue;
-  StepParams sp{};
-  if (fused_step) sp = *fused_step;
+  // pw_step_render: the step runs first, as its own launch on the same stream (the dynamics kernels
+  // of pw_kernels.cu: thousands of environments per CTA-wave), then the frames are rendered from the
+  // new state.  Stepping inside the render kernel (a few environments per CTA, one thread each)
+  // cost 0.3 ms per 2^16 environments; the separate launch costs ~10 us.
+  if (fused_step) {
+    const cudaError_t err = launch_steps(*fused_step, n_limit, stream);
+    if (err != cudaSuccess) return err;
+  }
   // persistent grid: enough CTAs to fill the machine several times over, never more than N
   int sm_count = 148;
   {
@@ -251,15 +273,8 @@ cudaError_t launch_render(const RenderParams& p, const StepParams* fused_step, i
   int64_t want = (int64_t)sm_count * 16;
   if ((p.N + 3) / 4 > want) want = (p.N + 3) / 4;
   const unsigned grid = (unsigned)(p.N < want ? p.N : want);
-#define PW_LAUNCH(T, F) k_render<T, F><<<grid, kRenderBlock, smem, stream>>>(p, sp)
-  if (p.dtype == 1) {
-    if (fused_step) PW_LAUNCH(float, true);
-    else PW_LAUNCH(float, false);
-  } else {
-    if (fused_step) PW_LAUNCH(uint8_t, true);
-    else PW_LAUNCH(uint8_t, false);
-  }
-#undef PW_LAUNCH
+  if (p.dtype == 1) k_render<float><<<grid, kRenderBlock, smem, stream>>>(p);
+  else k_render<uint8_t><<<grid, kRenderBlock, smem, stream>>>(p);
   return cudaGetLastError();
 }
 
@@ -267,14 +282,10 @@ cudaError_t configure_render_kernels() {
   // opt in to (almost) the full 227 KB of shared memory once per device; the kernels also use a
   // little static shared memory, which counts against the same limit
   const int cap = (int)kRenderMaxDynamicSmem;
-  cudaError_t err = cudaFuncSetAttribute(k_render<float, false>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+  cudaError_t err =
+      cudaFuncSetAttribute(k_render<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
   if (err == cudaSuccess)
-    err = cudaFuncSetAttribute(k_render<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
-  if (err == cudaSuccess)
-    err = cudaFuncSetAttribute(k_render<uint8_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
-  if (err == cudaSuccess)
-    err = cudaFuncSetAttribute(k_render<uint8_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+    err = cudaFuncSetAttribute(k_render<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
   return err;
 }
 
