@@ -252,7 +252,8 @@ PW_API int pw_render(PwEngine* engine, int64_t n_envs, const int32_t* puzzle_id,
               int pixels_per_cell, int border_width, int pad_h_cells, int pad_w_cells,
               void* stream);
 
-/* pw_step and pw_render of the new state fused in one launch (BASELINE config 5):
+/* pw_step and pw_render of the new state in one call (BASELINE config 5; the step kernel and
+ * the render kernel are launched back to back on `stream`):
  * what PushWorldEnv.step returns -- observation, reward, terminated, truncated
  * (gym_env.py:188-226). */
 PW_API int pw_step_render(PwEngine* engine, int64_t n_envs, const int32_t* puzzle_id,

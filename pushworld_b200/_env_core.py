@@ -1,7 +1,7 @@
 """Shared body of the two single-environment drop-ins (``gym_env.PushWorldEnv`` and
 ``dm_env.PushWorldEnv``): the reference duplicates this logic (python3/src/pushworld/
 gym_env.py:57-226 and dm_env.py:60-234); here both wrappers delegate to one class that drives
-the CUDA engine with a batch of ONE environment (fused step + render launch)."""
+the CUDA engine with a batch of ONE environment (one step + render call)."""
 
 from __future__ import annotations
 

@@ -381,7 +381,7 @@ class Engine:
                     pad_cells=None, steps: Optional[torch.Tensor] = None,
                     max_steps: Optional[int] = None, out: Optional[torch.Tensor] = None,
                     step_out: Optional[StepOutput] = None):
-        """Fused ``step`` + ``render`` of the new state (one launch)."""
+        """``step`` + ``render`` of the new state in one native call (two launches on one stream)."""
         n = self._chk_state(xy)
         pid_ptr, pid = self._sel(puzzle, n)
         self._chk(action, torch.uint8, (n,), "action")
