@@ -40,6 +40,9 @@ __device__ __forceinline__ uint32_t warp_sum(uint32_t v) {
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void flush_counts(const StepCounts& c, const StepParams& p,
                                              uint32_t* s_counters) {
+  // Launches without a counter vector (pw_step, pw_step_render) only report invalid actions, which
+  // are rare: one block-wide vote decides whether anything has to be reduced at all.
+  if (!p.counters && !__syncthreads_or(c.invalid != 0u)) return;
   if (p.counters || p.status) {
     const uint32_t c_term = warp_sum(c.terminated), c_moved = warp_sum(c.moved);
     const uint32_t c_dg = warp_sum(c.dgoals), c_invalid = warp_sum(c.invalid);

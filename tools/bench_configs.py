@@ -104,6 +104,17 @@ def main():
         out = eng.step(xy, 0, act)
         ms = time_ms(lambda: eng.step(xy, 0, act, out=out))
         results.append(report("cfg2 single step (pw_step): Road Block 2^18", n, ms, 16 * 3 + 6,
+                              {"unit": "env-steps", "note": "one Python call per step: launch-bound"}))
+        # the kernel itself: 50 steps captured in one CUDA graph (no host work between the launches)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=side):
+                for _ in range(50):
+                    eng.step(xy, 0, act, out=out)
+        ms = time_ms(graph.replay) / 50
+        results.append(report("cfg2 single step (pw_step) in a CUDA graph: Road Block 2^18", n, ms, 16 * 3 + 6,
                               {"unit": "env-steps"}))
 
     if want("cfg3"):
