@@ -196,7 +196,7 @@ def main():
         for dtype, size in (("float32", 4), ("uint8", 1)):
             obs = torch.empty((n, 100, 160, 3), dtype=torch.float32 if size == 4 else torch.uint8, device=dev)
             ms = time_ms(lambda: eng.step_render(xy, 0, act, dtype=dtype, out=obs))
-            results.append(report(f"cfg5 step+render fused: Road Block 2^16, {dtype} obs (100,160,3)",
+            results.append(report(f"cfg5 step + render (pw_step_render): Road Block 2^16, {dtype} obs (100,160,3)",
                                   n, ms, 100 * 160 * 3 * size + 54, {"unit": "frames"}))
             ms = time_ms(lambda: eng.render(xy, 0, dtype=dtype, out=obs))
             results.append(report(f"cfg5 render only: Road Block 2^16, {dtype}", n, ms,
