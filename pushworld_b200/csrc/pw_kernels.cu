@@ -230,10 +230,11 @@ __global__ void __launch_bounds__(kBlock, MIN_BLOCKS)
 // ------------------------------------------------------------------------------------------
 // Ring-board rollout (pw_board.cuh: ring_step): the plain-rollout shape (reward + terminated per
 // step, nothing else) of a single puzzle whose board leaves P spare bits in a uint32.  The loop
-// is written out here instead of going through run_steps_sim because every instruction of it is
-// on the ALU pipe's critical path: one rotate per object, predicate-only push logic, running
-// output pointers, and (kG1: one goal object, the common case) reward and terminated decided by
-// a single compare.
+// is written out here instead of going through run_steps_sim because the integer ALU pipe is the
+// bound: the rule itself (one rotate per object, board tests, predicate logic,
+// selects) has to run there, so the bookkeeping around it is kept off that pipe -- addresses, the
+// terminated flag of the one-goal case (kG1) and everything derived from it are multiply-adds,
+// and actions come out of shared-memory tiles filled by cp.async a block of steps ahead.
 // ------------------------------------------------------------------------------------------
 template <int NMAX, bool kG1>
 __device__ __forceinline__ void run_ring_lean(const Board<NMAX, uint32_t>& s, const StepParams& p,
