@@ -14,9 +14,23 @@ _LIB = None
 
 
 def build(force=False):
+    """gcc build of the C restatement; serialised by a file lock and renamed into place so that
+    concurrent callers (several test or bench processes) never load a half-written library."""
+    import fcntl
+
     src = os.path.join(HERE, "pw_oracle.c")
-    if force or not os.path.exists(SO) or os.path.getmtime(SO) < os.path.getmtime(src):
-        subprocess.check_call(["make", "-s", "-B", "-C", HERE, "libpw_oracle.so"])
+    stale = lambda: not os.path.exists(SO) or os.path.getmtime(SO) < os.path.getmtime(src)
+    if not force and not stale():
+        return SO
+    with open(os.path.join(HERE, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if force or stale():
+                tmp = f"libpw_oracle.so.tmp.{os.getpid()}"
+                subprocess.check_call(["make", "-s", "-B", "-C", HERE, f"OUT={tmp}", "libpw_oracle.so"])
+                os.replace(os.path.join(HERE, tmp), SO)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return SO
 
 

@@ -33,29 +33,67 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found; the pushworld_b200 CUDA library cannot be built")
 
 
+STAMP_PATH = LIB_PATH + ".sha256"
+
+
+def _sources_digest() -> str:
+    """sha256 over the native sources and the public header (content, not timestamps: a checkout
+    or a copy of the tree must not trigger a rebuild on every rank of a multi-GPU launch)."""
+    import hashlib
+
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    paths = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC))
+    paths.append(os.path.join(os.path.dirname(PKG), "include", "pushworld_b200.h"))
+    for path in paths:
+        if os.path.isfile(path):
+            h.update(os.path.basename(path).encode())
+            with open(path, "rb") as f:
+                h.update(f.read())
+    return h.hexdigest()
+
+
 def _stale() -> bool:
-    if not os.path.exists(LIB_PATH):
+    if not os.path.exists(LIB_PATH) or not os.path.exists(STAMP_PATH):
         return True
-    built = os.path.getmtime(LIB_PATH)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
-    deps.append(os.path.join(os.path.dirname(PKG), "include", "pushworld_b200.h"))
-    return any(os.path.getmtime(d) > built for d in deps)
+    with open(STAMP_PATH) as f:
+        return f.read().strip() != _sources_digest()
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compiles the CUDA library if it is missing or older than its sources."""
+    """Compiles the CUDA library if it is missing or older than its sources.
+
+    Safe to call from several processes at once (one rank per GPU under torchrun): an exclusive
+    file lock serialises the builders, staleness is re-checked under the lock, and the compiler
+    writes to a private temporary file that is renamed into place, so no process can ever load a
+    partially written library."""
     if not force and not _stale():
         return LIB_PATH
+    import fcntl
+
     os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [_nvcc(), *NVCC_FLAGS]
-    if verbose:
-        cmd += ["-Xptxas", "-v"]
-    cmd += [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB_PATH]
-    proc = subprocess.run(cmd, capture_output=True, text=True)
-    if proc.returncode != 0:
-        raise RuntimeError(f"nvcc failed:\n{' '.join(cmd)}\n{proc.stdout}\n{proc.stderr}")
-    if verbose:
-        print(proc.stderr, file=sys.stderr)
+    with open(os.path.join(LIB_DIR, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not _stale():  # another process built it while this one waited
+                return LIB_PATH
+            tmp = f"{LIB_PATH}.tmp.{os.getpid()}"
+            cmd = [_nvcc(), *NVCC_FLAGS]
+            if verbose:
+                cmd += ["-Xptxas", "-v"]
+            cmd += [os.path.join(CSRC, s) for s in SOURCES] + ["-o", tmp]
+            proc = subprocess.run(cmd, capture_output=True, text=True)
+            if proc.returncode != 0:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                raise RuntimeError(f"nvcc failed:\n{' '.join(cmd)}\n{proc.stdout}\n{proc.stderr}")
+            os.replace(tmp, LIB_PATH)
+            with open(STAMP_PATH + f".tmp.{os.getpid()}", "w") as f:
+                f.write(_sources_digest() + "\n")
+            os.replace(STAMP_PATH + f".tmp.{os.getpid()}", STAMP_PATH)
+            if verbose:
+                print(proc.stderr, file=sys.stderr)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB_PATH
 
 

@@ -22,13 +22,15 @@ def lib():
         csrc = os.path.join(REPO, "pushworld_b200", "csrc")
         deps = [src] + [os.path.join(csrc, f) for f in ("pw_core.cuh", "pw_render_core.cuh", "pw_board.cuh")]
         if not os.path.exists(so) or os.path.getmtime(so) < max(map(os.path.getmtime, deps)):
+            tmp = f"{so}.tmp.{os.getpid()}"  # renamed into place: safe with parallel test processes
             subprocess.check_call(
                 [
                     "g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-Wno-unknown-pragmas",
                     "-x", "c++", "-I", os.path.join(REPO, "pushworld_b200", "csrc"),
-                    src, "-o", so,
+                    src, "-o", tmp,
                 ]
             )
+            os.replace(tmp, so)
         _LIB = ctypes.CDLL(so)
         _LIB.hc_walk.restype = ctypes.c_int
     return _LIB
