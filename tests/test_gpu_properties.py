@@ -3,7 +3,8 @@ hours) and metamorphic checks under the 8 grid symmetries:
 
 * config 2 (2^18 Road Block environments x 1024 steps): a rollout split into chunks equals the
   rollout in one launch; permuting environments permutes the outputs; counters equal reductions of
-  the per-step outputs; a sample of columns equals the oracle;
+  the per-step outputs; the ring-board kernel and the edge-mask board kernel agree on all 2.7e8
+  steps; a sample of columns equals the oracle;
 * config 4 (expansion): successors of an action-major expansion equal single steps;
 * symmetries (python3/src/pushworld/transform.py + test_transform.py restated): rotating /
   flipping a puzzle and mapping the actions accordingly gives the rotated / flipped trajectory.
@@ -58,6 +59,17 @@ def test_config2_full_size_rollout_properties():
     vals = torch.unique(rew_a).cpu().numpy()
     assert set(vals.tolist()) <= {float(np.float32(-0.01)), float(np.float32(0.99)),
                                   float(np.float32(-1.01)), 10.0}
+    # 2b. two implementations, one answer: asking for one more output (dgoals) takes the launch off
+    # the ring-board kernel and onto the edge-mask board kernel (pw_board.cuh: board_step)
+    xy_c = engine.new_state(n)
+    engine.reset(xy_c, 0)
+    rew_c = torch.empty_like(rew_a)
+    term_c = torch.empty_like(term_a)
+    dg_c = torch.empty((T, n), dtype=torch.int8, device="cuda")
+    engine.rollout(xy_c, 0, actions, reward=rew_c, terminated=term_c, dgoals=dg_c)
+    assert torch.equal(xy_a, xy_c) and torch.equal(rew_a, rew_c) and torch.equal(term_a, term_c)
+    assert int(cnt_a[3]) == int(dg_c.clamp(min=0).sum(dtype=torch.int64))
+    del xy_c, rew_c, term_c, dg_c
     # 3. permutation equivariance on a slice of the batch
     m = 1 << 14
     perm = torch.randperm(m, device="cuda", generator=gen)
