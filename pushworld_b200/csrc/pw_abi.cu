@@ -12,6 +12,7 @@
 
 #include "../../include/pushworld_b200.h"
 #include "pw_board.cuh"
+#include "pw_fast.cuh"
 #include "pw_core.cuh"
 #include "pw_host.h"
 #include "pw_internal.h"
@@ -31,7 +32,9 @@ static int cuda_error(cudaError_t err, const char* what) {
 }
 
 struct PuzzleInfo {
-  int width, height, n, g, size_u64;
+  int width, height, n, g;
+  int size_u64;   // geometry blob + collision bit tables, as stored on the device
+  int blob_u64;   // geometry blob alone (what the caller passed in)
   uint32_t flags;
 };
 
@@ -56,6 +59,7 @@ class DeviceGuard {
 struct PwEngine {
   int device = 0;
   int n_max = 0, max_w = 0, max_h = 0, max_cells = 0, max_blob_u64 = 0;
+  int max_packed_u64 = 0;  // largest geometry blob + collision tables (shared-memory staging)
   std::vector<pw::PuzzleInfo> puzzles;
   uint64_t* d_blob = nullptr;
   uint32_t* d_off = nullptr;
@@ -189,6 +193,7 @@ int pw_engine_create(const void* blob, size_t blob_bytes, const uint32_t* offset
     info.g = (int)(h[2] >> 16);
     info.flags = h[3];
     info.size_u64 = (int)h[7];
+    info.blob_u64 = (int)h[7];
     const size_t n_desc = (size_t)info.n + (size_t)info.g;
     bool ok = h[0] == PW_TABLE_MAGIC && info.n >= 1 && info.n <= PW_MAX_OBJECTS &&
               info.g < info.n + 1 && info.width >= 3 && info.width <= PW_MAX_WIDTH &&
@@ -228,6 +233,28 @@ int pw_engine_create(const void* blob, size_t blob_bytes, const uint32_t* offset
   e->board_bits_all = 0;
   for (int b : e->board_bits) e->board_bits_all = b > e->board_bits_all ? b : e->board_bits_all;
 
+  // Device layout of a puzzle: its geometry blob, immediately followed by the collision bit tables
+  // derived from it (pw_fast.cuh).  Kernels find the tables at base + header size.
+  std::vector<uint64_t> packed;
+  std::vector<uint32_t> packed_off((size_t)num_puzzles);
+  e->max_packed_u64 = 0;
+  for (int p = 0; p < num_puzzles; ++p) {
+    PuzzleInfo& info = e->puzzles[(size_t)p];
+    const uint64_t* src = reinterpret_cast<const uint64_t*>(bytes) + offsets_u64[p];
+    packed_off[(size_t)p] = (uint32_t)packed.size();
+    packed.insert(packed.end(), src, src + info.blob_u64);
+    build_fast_table(src, &packed);
+    info.size_u64 = (int)(packed.size() - packed_off[(size_t)p]);
+    e->max_packed_u64 = info.size_u64 > e->max_packed_u64 ? info.size_u64 : e->max_packed_u64;
+  }
+  if (packed.size() > 0xffffffffull) {
+    delete e;
+    return set_error(PW_E_LIMIT, "puzzle tables exceed 32 GiB");
+  }
+  blob = packed.data();
+  blob_bytes = packed.size() * 8;
+  offsets_u64 = packed_off.data();
+
   DeviceGuard guard(device);
   cudaError_t err = cudaSetDevice(device);
   if (err == cudaSuccess) err = cudaMalloc(&e->d_blob, blob_bytes);
@@ -263,7 +290,7 @@ int pw_engine_create(const void* blob, size_t blob_bytes, const uint32_t* offset
     err = upload_palette(&pal[0][0], &palf[0][0], 13);
   }
   if (err == cudaSuccess) {
-    const size_t need = (size_t)e->max_blob_u64 * 8 + (size_t)e->n_max * 2 * 128 * sizeof(int) + 64;
+    const size_t need = (size_t)e->max_packed_u64 * 8 + (size_t)e->n_max * 2 * 128 * sizeof(int) + 64;
     err = configure_kernels(need > 48 * 1024 ? need : 48 * 1024);
   }
   if (err == cudaSuccess) err = configure_render_kernels();

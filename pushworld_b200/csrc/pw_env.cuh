@@ -16,6 +16,7 @@
 #include <stdint.h>
 
 #include "pw_core.cuh"
+#include "pw_fast.cuh"
 
 namespace pw {
 
@@ -38,7 +39,9 @@ struct GlobalTable {
 template <class Table>
 struct EnvBase {
   Table t;
+  Table ft;  // collision bit tables of the same puzzle (pw_fast.cuh): stored right after the blob
   int n_, g_, w_, h_, wall_off_, awall_off_, desc_word_;
+  __device__ __forceinline__ uint64_t fast(int k) const { return ft.row(k); }
   __device__ __forceinline__ void init_header(Table table) {
     t = table;
     const uint32_t dims = t.word(kHdrDims), counts = t.word(kHdrCounts);
@@ -49,8 +52,9 @@ struct EnvBase {
     wall_off_ = (int)t.word(kHdrWallOff);
     awall_off_ = (int)t.word(kHdrAwallOff);
     desc_word_ = (int)t.word(kHdrObjOff) * 2;
+    ft = Table{t.base + t.word(kHdrSizeU64)};
   }
-  // points the view at another puzzle's table (same address space)
+  // points the view at another puzzle's tables (same address space)
   __device__ __forceinline__ void retarget(const uint64_t* base) { init_header(Table{base}); }
   __device__ __forceinline__ int n() const { return n_; }
   __device__ __forceinline__ int g() const { return g_; }

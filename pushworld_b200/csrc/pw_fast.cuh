@@ -1,0 +1,173 @@
+// pw_fast.cuh -- collision bit tables and the transition rule that reads them.
+//
+// The reference never evaluates geometry inside get_next_state: PushWorldPuzzle.__init__
+// precomputes, per action, the positions at which an object is stopped by the walls and the
+// relative positions at which one movable pushes another (puzzle.py:259-308, 522-593), and a step
+// is a handful of set look-ups (puzzle.py:348-394).  This file is that design with bitmaps instead
+// of hash sets.  The tables are DERIVED from the geometry blob at engine creation by evaluating
+// the exact predicates of pw_core.cuh (static_blocked, shapes_overlap) at every position of a
+// finite window outside of which they are provably false, so
+//     step_tab(env, a) == step(env, a)        for every state, on or off the grid.
+// All 223 benchmark puzzles together need 0.63 MB of tables (largest: 23 KB).
+//
+// Layout of one puzzle's table F (u64 units, offsets relative to F):
+//   F[0]                 n
+//   F[1 + i*n + j]       pair (pusher i, pushee j >= 1, i != j):
+//                          low word  = offset of the bitmap
+//                          high word = Ww | Hw << 8 | w_j << 17 | h_j << 24
+//                        with Ww = w_i + w_j + 1, Hw = h_i + h_j + 1: the window of relative
+//                        positions r = p_j - p_i, -w_j <= rx <= w_i, -h_j <= ry <= h_i; bit
+//                        (a * Hw + ry + h_j) * Ww + rx + w_j  <=>  i, moved by action a, pushes j
+//   F[1 + n*n + j]       walls vs object j (the agent against aw UNION w, puzzle.py:273):
+//                          low word  = offset of the bitmap
+//                          high word = xmax | ymax << 6 | W << 18   (xmax = W - w_j, ymax = H - h_j)
+//                        bit ((y * W + x) << 2 | a)  <=>  j at (x, y) is stopped when moved by a;
+//                        positions whose bounding box leaves the grid are never stopped (:557-561)
+#pragma once
+#include <stdint.h>
+
+#include "pw_core.cuh"
+
+namespace pw {
+
+// `env.fast(k)` = F[k].  Is object j at (x, y) stopped by the static cells when moved by action a?
+template <class Env>
+PW_HD bool tab_wall(const Env& env, int nn1, int j, uint32_t a, int x, int y) {
+  const uint64_t wd = env.fast(nn1 + j);
+  const uint32_t hi = (uint32_t)(wd >> 32);
+  if ((uint32_t)x > (hi & 63u) || (uint32_t)y > ((hi >> 6) & 0xfffu)) return false;
+  const uint32_t idx = (((uint32_t)y * (hi >> 18) + (uint32_t)x) << 2) | a;
+  return (env.fast((int)((uint32_t)wd + (idx >> 6))) >> (idx & 63u)) & 1ull;
+}
+
+// Does pusher i (descriptor index base = 1 + i*n), moved by action a, push j at relative position
+// (rx, ry) = p_j - p_i?
+template <class Env>
+PW_HD bool tab_pushes(const Env& env, int pair_index, uint32_t a, int rx, int ry) {
+  const uint64_t pd = env.fast(pair_index);
+  const uint32_t hi = (uint32_t)(pd >> 32);
+  const uint32_t Ww = hi & 0xffu, Hw = (hi >> 8) & 0x1ffu;
+  const uint32_t ux = (uint32_t)(rx + (int)((hi >> 17) & 0x7fu)), uy = (uint32_t)(ry + (int)(hi >> 24));
+  if (ux >= Ww || uy >= Hw) return false;
+  const uint32_t idx = (a * Hw + uy) * Ww + ux;
+  return (env.fast((int)((uint32_t)pd + (idx >> 6))) >> (idx & 63u)) & 1ull;
+}
+
+// One transition on the tables.  Same contract as step() (pw_core.cuh): returns the moved-object
+// bitmask, 0 if nothing moved.  The scan of a pusher over the other objects is branch-free per
+// object (one pair look-up each); the wall look-ups of the objects it hits come after the scan.
+template <class Env>
+PW_HD uint32_t step_tab(Env& env, int action) {
+  if ((unsigned)action > 3u) return 0;  // invalid actions are no-ops (counted by the caller)
+  const uint32_t a = (uint32_t)action;
+  const int n = env.n();
+  const int nn1 = 1 + n * n;
+  if (tab_wall(env, nn1, 0, a, env.x(0), env.y(0))) return 0;  // puzzle.py:353-354
+  const int jend = Env::kStaticN ? Env::kStaticN : n;
+  uint32_t pushed = 1u, frontier = 1u;
+  while (frontier) {
+    const int i = pw_ffs(frontier) - 1;
+    frontier &= frontier - 1;
+    const int xi = env.x_dyn(i), yi = env.y_dyn(i);
+    const int base = 1 + i * n;
+    uint32_t hits = 0;
+#pragma unroll
+    for (int j = 1; j < jend; ++j) {
+      if (Env::kStaticN && j >= n) break;
+      // (the descriptor of the pair (i, i) is zero: an empty window)
+      const bool push = tab_pushes(env, base + j, a, env.x(j) - xi, env.y(j) - yi);
+      hits |= push ? (1u << j) : 0u;
+    }
+    hits &= ~pushed;
+    pushed |= hits;
+    frontier |= hits;
+    while (hits) {  // transitive stopping, puzzle.py:376-379
+      const int j = pw_ffs(hits) - 1;
+      hits &= hits - 1;
+      if (tab_wall(env, nn1, j, a, env.x_dyn(j), env.y_dyn(j))) return 0;
+    }
+  }
+  env.translate(pushed, action_dx(action), action_dy(action));
+  return pushed;
+}
+
+}  // namespace pw
+
+// ---- host-side construction (engine creation, tests/hostcheck) -----------------------------
+#include <vector>
+
+namespace pw {
+
+// Geometry view of a blob for the exact predicates of pw_core.cuh.
+struct FastBuildEnv {
+  const uint64_t* base;
+  int w_, h_;
+  PW_HD uint64_t row(int off) const { return base[off]; }
+  PW_HD int width() const { return w_; }
+  PW_HD int height() const { return h_; }
+};
+
+// Appends the table of the puzzle in `blob` to `out` (its offsets are relative to its own start).
+inline void build_fast_table(const uint64_t* blob, std::vector<uint64_t>* out) {
+  const uint32_t* words = reinterpret_cast<const uint32_t*>(blob);
+  const int W = (int)(words[kHdrDims] & 0xffffu), H = (int)(words[kHdrDims] >> 16);
+  const int n = (int)(words[kHdrCounts] & 0xffffu);
+  const int wall_off = (int)words[kHdrWallOff], awall_off = (int)words[kHdrAwallOff];
+  const int desc_word = (int)words[kHdrObjOff] * 2;
+  const FastBuildEnv env{blob, W, H};
+  const size_t start = out->size();
+  out->resize(start + 1 + (size_t)n * n + n, 0ull);
+  (*out)[start] = (uint64_t)n;
+  auto set_bit = [&](size_t off, uint32_t idx) { (*out)[start + off + (idx >> 6)] |= 1ull << (idx & 63u); };
+  // walls
+  for (int j = 0; j < n; ++j) {
+    const uint32_t dj = words[desc_word + 4 * j];
+    const int w = desc_w(dj), h = desc_h(dj);
+    const int xmax = W - w, ymax = H - h;
+    const size_t off = out->size() - start;
+    if (xmax < 0 || ymax < 0) {  // larger than the grid: never inside it, never stopped
+      out->resize(out->size() + 1, 0ull);
+      (*out)[start + 1 + (size_t)n * n + j] = (uint64_t)off;  // xmax = ymax = 0, W = 0 -> one cell, all zero
+      continue;
+    }
+    const uint32_t bits = (uint32_t)W * (uint32_t)H * 4u;
+    out->resize(out->size() + (bits + 63u) / 64u, 0ull);
+    for (int y = 0; y <= ymax; ++y)
+      for (int x = 0; x <= xmax; ++x)
+        for (int a = 0; a < 4; ++a)
+          if (static_blocked(env, dj, x, y, action_dx(a), action_dy(a), j == 0 ? awall_off : wall_off))
+            set_bit(off, (uint32_t)((y * W + x) << 2 | a));
+    (*out)[start + 1 + (size_t)n * n + j] =
+        (uint64_t)off | ((uint64_t)((uint32_t)xmax | ((uint32_t)ymax << 6) | ((uint32_t)W << 18)) << 32);
+  }
+  // pairs
+  for (int i = 0; i < n; ++i) {
+    const uint32_t di = words[desc_word + 4 * i];
+    const int wi = desc_w(di), hi = desc_h(di);
+    for (int j = 1; j < n; ++j) {
+      if (j == i) continue;
+      const uint32_t dj = words[desc_word + 4 * j];
+      const int wj = desc_w(dj), hj = desc_h(dj);
+      const int Ww = wi + wj + 1, Hw = hi + hj + 1;
+      const size_t off = out->size() - start;
+      const uint32_t bits = 4u * (uint32_t)Ww * (uint32_t)Hw;
+      out->resize(out->size() + (bits + 63u) / 64u, 0ull);
+      for (int a = 0; a < 4; ++a) {
+        const int dx = action_dx(a), dy = action_dy(a);
+        for (int uy = 0; uy < Hw; ++uy)
+          for (int ux = 0; ux < Ww; ++ux) {
+            const int rx = ux - wj, ry = uy - hj;  // p_j - p_i
+            // puzzle.py:567-593: the moved pusher overlaps j and the unmoved one does not
+            if (shapes_overlap(env, di, dj, rx - dx, ry - dy) && !shapes_overlap(env, di, dj, rx, ry))
+              set_bit(off, (uint32_t)((a * Hw + uy) * Ww + ux));
+          }
+      }
+      (*out)[start + 1 + (size_t)i * n + j] =
+          (uint64_t)off | ((uint64_t)((uint32_t)Ww | ((uint32_t)Hw << 8) | ((uint32_t)wj << 17) |
+                                      ((uint32_t)hj << 24))
+                           << 32);
+    }
+  }
+}
+
+}  // namespace pw

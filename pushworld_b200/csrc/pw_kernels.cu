@@ -536,7 +536,7 @@ __device__ __forceinline__ void run_expand(Env& env, const ExpandParams& p, int6
   const int g = env.g();
 #pragma unroll 1
   for (int a = 0; a < 4; ++a) {
-    const uint32_t moved = step(env, a);
+    const uint32_t moved = step_tab(env, a);
     const int64_t s = (int64_t)a * p.N + e;
     env.store(p.x_out, p.y_out, p.stride_out, s);
     if (p.moved) p.moved[s] = moved;

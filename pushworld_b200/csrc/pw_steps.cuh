@@ -6,6 +6,7 @@
 #include <stdint.h>
 
 #include "pw_core.cuh"
+#include "pw_fast.cuh"
 #include "pw_internal.h"
 
 namespace pw {
@@ -32,14 +33,15 @@ __device__ __forceinline__ int draw_puzzle(uint64_t seed, int64_t env, uint32_t 
   return (int)(((h >> 32) * (uint64_t)num_puzzles) >> 32);
 }
 
-// Adaptor: an Env policy (pw_env.cuh) driven by the general rule of pw_core.cuh.
+// Adaptor: an Env policy (pw_env.cuh) driven by the general rule, read from the collision bit
+// tables (pw_fast.cuh: step_tab == pw_core.cuh's step on every state).
 template <class Env>
 struct GeneralSim {
   Env& env;
   __device__ __forceinline__ void load(const StepParams& p, int64_t e) { env.load(p.x, p.y, p.stride, e); }
   __device__ __forceinline__ void store(const StepParams& p, int64_t e) { env.store(p.x, p.y, p.stride, e); }
   __device__ __forceinline__ void load_initial() { env.load_initial(); }
-  __device__ __forceinline__ uint32_t do_step(int a) { return step(env, a); }
+  __device__ __forceinline__ uint32_t do_step(int a) { return step_tab(env, a); }
   __device__ __forceinline__ int achieved() const { return achieved_goals(env); }
   __device__ __forceinline__ int goals() const { return env.g(); }
   // new episode on a freshly drawn puzzle (only table views that can be re-pointed support it)

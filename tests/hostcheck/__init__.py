@@ -20,7 +20,7 @@ def lib():
         so = os.path.join(out_dir, "libhostcheck.so")
         src = os.path.join(HERE, "hostcheck.cpp")
         csrc = os.path.join(REPO, "pushworld_b200", "csrc")
-        deps = [src] + [os.path.join(csrc, f) for f in ("pw_core.cuh", "pw_render_core.cuh", "pw_board.cuh")]
+        deps = [src] + [os.path.join(csrc, f) for f in ("pw_core.cuh", "pw_render_core.cuh", "pw_board.cuh", "pw_fast.cuh")]
         if not os.path.exists(so) or os.path.getmtime(so) < max(map(os.path.getmtime, deps)):
             tmp = f"{so}.tmp.{os.getpid()}"  # renamed into place: safe with parallel test processes
             subprocess.check_call(
@@ -52,6 +52,25 @@ def walk(blob: bytes, state, actions):
     got_n = lib().hc_walk(p(buf), p(x), p(y), p(acts), T, p(xs), p(ys), p(moved), p(ach))
     assert got_n == n
     return np.stack([xs, ys], axis=-1), moved, ach
+
+
+def walk_tab(blob: bytes, state, actions):
+    """`walk` through the collision bit tables (pw_fast.cuh); also returns the table size in bytes."""
+    buf = np.frombuffer(blob, dtype=np.uint64).copy()
+    n = len(state)
+    x = np.array([p[0] for p in state], dtype=np.int32)
+    y = np.array([p[1] for p in state], dtype=np.int32)
+    acts = np.asarray(actions, dtype=np.uint8)
+    T = len(acts)
+    xs = np.zeros((T, n), np.int32)
+    ys = np.zeros((T, n), np.int32)
+    moved = np.zeros(T, np.uint32)
+    ach = np.zeros(T, np.int32)
+    size = ctypes.c_int(0)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    got_n = lib().hc_walk_tab(p(buf), p(x), p(y), p(acts), T, p(xs), p(ys), p(moved), p(ach), ctypes.byref(size))
+    assert got_n == n
+    return np.stack([xs, ys], axis=-1), moved, ach, size.value * 8
 
 
 def board_walk(blob: bytes, state, actions, word_bits: int = 64):

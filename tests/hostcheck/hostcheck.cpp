@@ -7,6 +7,7 @@
 
 #include "pw_board.cuh"
 #include "pw_core.cuh"
+#include "pw_fast.cuh"
 #include "pw_render_core.cuh"
 
 namespace {
@@ -15,9 +16,11 @@ struct HostEnv {
   static constexpr int kStaticN = 0;
   static constexpr int kUnroll = 1;
   const uint64_t* base;
+  const uint64_t* ftab = nullptr;  // collision bit tables (pw_fast.cuh), built by hc_walk_tab
   int n_, g_, w_, h_, wall_off_, awall_off_, desc_word_;
   int* px;
   int* py;
+  uint64_t fast(int k) const { return ftab[k]; }
   uint32_t word(int i) const { return reinterpret_cast<const uint32_t*>(base)[i]; }
   void init(const uint64_t* b, int* x, int* y) {
     base = b;
@@ -169,6 +172,25 @@ void hc_render_u8(const uint64_t* blob, const int* x, const int* y, int ppc, int
           px[2] = palette[pal * 3 + 2];
         }
     }
+}
+
+// The same walk through the table-driven rule (pw_fast.cuh: tables built from the blob here, then
+// step_tab); also returns the table size in u64 units through *table_u64.
+int hc_walk_tab(const uint64_t* blob, int* x, int* y, const uint8_t* actions, int n_actions,
+                int* xs, int* ys, uint32_t* moved, int* achieved, int* table_u64) {
+  std::vector<uint64_t> table;
+  pw::build_fast_table(blob, &table);
+  if (table_u64) *table_u64 = (int)table.size();
+  HostEnv env;
+  env.init(blob, x, y);
+  env.ftab = table.data();
+  for (int t = 0; t < n_actions; ++t) {
+    moved[t] = pw::step_tab(env, actions[t]);
+    achieved[t] = pw::achieved_goals(env);
+    memcpy(xs + (size_t)t * env.n(), x, sizeof(int) * env.n());
+    memcpy(ys + (size_t)t * env.n(), y, sizeof(int) * env.n());
+  }
+  return env.n();
 }
 
 // Applies `n_actions` actions in sequence to one environment, recording after every action the

@@ -22,6 +22,10 @@ def _check(golden, key, tag):
     ref = golden.arr(key, f"{tag}_states").astype(np.int32)
     states, moved, ach = hostcheck.walk(blob, parsed.initial_state, actions)
     assert np.array_equal(states, ref[1:]), key
+    # the table-driven rule (pw_fast.cuh) must agree with the geometric rule transition by transition
+    states_t, moved_t, ach_t, table_bytes = hostcheck.walk_tab(blob, parsed.initial_state, actions)
+    assert np.array_equal(states_t, states) and np.array_equal(moved_t, moved) and np.array_equal(ach_t, ach), key
+    assert table_bytes < 64 * 1024, (key, table_bytes)
     assert np.array_equal(ach, golden.arr(key, f"{tag}_achieved")[1:].astype(np.int32)), key
     # the moved mask is exactly the set of objects whose position changed
     changed = (ref[1:] != ref[:-1]).any(axis=2)
@@ -167,6 +171,8 @@ def test_general_rule_matches_oracle_on_irregular_puzzles():
         blob = tables.compile_text(text)
         actions = rng.integers(0, 4, size=120).astype(np.uint8)
         states, moved, ach = hostcheck.walk(blob, oracle.initial_state, actions)
+        states_t, moved_t, ach_t, _ = hostcheck.walk_tab(blob, oracle.initial_state, actions)
+        assert np.array_equal(states_t, states) and np.array_equal(moved_t, moved) and np.array_equal(ach_t, ach), text
         state = oracle.initial_state
         for t, a in enumerate(actions):
             state, moved_idx = oracle.get_next_state_and_moved(state, int(a))
