@@ -23,6 +23,10 @@ namespace pw {
 struct SharedTable {
   const uint64_t* base;
   __device__ __forceinline__ uint64_t row(int off) const { return base[off]; }
+  __device__ __forceinline__ uint64_t qword(uint32_t off) const { return base[off]; }  // unsigned: one IMAD.WIDE
+  __device__ __forceinline__ uint32_t dword(uint32_t i) const {
+    return reinterpret_cast<const uint32_t*>(base)[i];
+  }
   __device__ __forceinline__ uint32_t word(int i) const {
     return reinterpret_cast<const uint32_t*>(base)[i];
   }
@@ -31,6 +35,10 @@ struct SharedTable {
 struct GlobalTable {
   const uint64_t* base;
   __device__ __forceinline__ uint64_t row(int off) const { return __ldg(base + off); }
+  __device__ __forceinline__ uint64_t qword(uint32_t off) const { return __ldg(base + off); }
+  __device__ __forceinline__ uint32_t dword(uint32_t i) const {
+    return __ldg(reinterpret_cast<const uint32_t*>(base) + i);
+  }
   __device__ __forceinline__ uint32_t word(int i) const {
     return __ldg(reinterpret_cast<const uint32_t*>(base) + i);
   }
@@ -41,7 +49,8 @@ struct EnvBase {
   Table t;
   Table ft;  // collision bit tables of the same puzzle (pw_fast.cuh): stored right after the blob
   int n_, g_, w_, h_, wall_off_, awall_off_, desc_word_;
-  __device__ __forceinline__ uint64_t fast(int k) const { return ft.row(k); }
+  __device__ __forceinline__ uint64_t fast(uint32_t k) const { return ft.qword(k); }
+  __device__ __forceinline__ uint32_t fast32(uint32_t k) const { return ft.dword(k); }
   __device__ __forceinline__ void init_header(Table table) {
     t = table;
     const uint32_t dims = t.word(kHdrDims), counts = t.word(kHdrCounts);
@@ -52,7 +61,11 @@ struct EnvBase {
     wall_off_ = (int)t.word(kHdrWallOff);
     awall_off_ = (int)t.word(kHdrAwallOff);
     desc_word_ = (int)t.word(kHdrObjOff) * 2;
-    ft = Table{t.base + t.word(kHdrSizeU64)};
+    // an opaque per-thread pointer: otherwise every table address is rebuilt from the uniform blob
+    // pointer plus the puzzle offset (four instructions instead of one IMAD.WIDE)
+    const uint64_t* fast_base = t.base + t.word(kHdrSizeU64);
+    asm volatile("" : "+l"(fast_base));
+    ft = Table{fast_base};
   }
   // points the view at another puzzle's tables (same address space)
   __device__ __forceinline__ void retarget(const uint64_t* base) { init_header(Table{base}); }

@@ -30,27 +30,28 @@
 
 namespace pw {
 
-// `env.fast(k)` = F[k].  Is object j at (x, y) stopped by the static cells when moved by action a?
+// `env.fast(k)` = F[k]; `env.fast32(k)` = 32-bit word k of F (little endian: bit b of the bitmap at
+// u64 offset o is bit b & 31 of 32-bit word 2 * o + (b >> 5)).  Is object j at (x, y) stopped by the static cells when moved by action a?
 template <class Env>
-PW_HD bool tab_wall(const Env& env, int nn1, int j, uint32_t a, int x, int y) {
+PW_HD bool tab_wall(const Env& env, uint32_t nn1, uint32_t j, uint32_t a, int x, int y) {
   const uint64_t wd = env.fast(nn1 + j);
   const uint32_t hi = (uint32_t)(wd >> 32);
   if ((uint32_t)x > (hi & 63u) || (uint32_t)y > ((hi >> 6) & 0xfffu)) return false;
   const uint32_t idx = (((uint32_t)y * (hi >> 18) + (uint32_t)x) << 2) | a;
-  return (env.fast((int)((uint32_t)wd + (idx >> 6))) >> (idx & 63u)) & 1ull;
+  return (env.fast32(((uint32_t)wd << 1) + (idx >> 5)) >> (idx & 31u)) & 1u;
 }
 
 // Does pusher i (descriptor index base = 1 + i*n), moved by action a, push j at relative position
 // (rx, ry) = p_j - p_i?
 template <class Env>
-PW_HD bool tab_pushes(const Env& env, int pair_index, uint32_t a, int rx, int ry) {
+PW_HD bool tab_pushes(const Env& env, uint32_t pair_index, uint32_t a, int rx, int ry) {
   const uint64_t pd = env.fast(pair_index);
   const uint32_t hi = (uint32_t)(pd >> 32);
   const uint32_t Ww = hi & 0xffu, Hw = (hi >> 8) & 0x1ffu;
   const uint32_t ux = (uint32_t)(rx + (int)((hi >> 17) & 0x7fu)), uy = (uint32_t)(ry + (int)(hi >> 24));
   if (ux >= Ww || uy >= Hw) return false;
   const uint32_t idx = (a * Hw + uy) * Ww + ux;
-  return (env.fast((int)((uint32_t)pd + (idx >> 6))) >> (idx & 63u)) & 1ull;
+  return (env.fast32(((uint32_t)pd << 1) + (idx >> 5)) >> (idx & 31u)) & 1u;
 }
 
 // One transition on the tables.  Same contract as step() (pw_core.cuh): returns the moved-object
@@ -61,21 +62,21 @@ PW_HD uint32_t step_tab(Env& env, int action) {
   if ((unsigned)action > 3u) return 0;  // invalid actions are no-ops (counted by the caller)
   const uint32_t a = (uint32_t)action;
   const int n = env.n();
-  const int nn1 = 1 + n * n;
-  if (tab_wall(env, nn1, 0, a, env.x(0), env.y(0))) return 0;  // puzzle.py:353-354
+  const uint32_t nn1 = 1u + (uint32_t)(n * n);
+  if (tab_wall(env, nn1, 0u, a, env.x(0), env.y(0))) return 0;  // puzzle.py:353-354
   const int jend = Env::kStaticN ? Env::kStaticN : n;
   uint32_t pushed = 1u, frontier = 1u;
   while (frontier) {
     const int i = pw_ffs(frontier) - 1;
     frontier &= frontier - 1;
     const int xi = env.x_dyn(i), yi = env.y_dyn(i);
-    const int base = 1 + i * n;
+    const uint32_t base = 1u + (uint32_t)(i * n);
     uint32_t hits = 0;
 #pragma unroll
     for (int j = 1; j < jend; ++j) {
       if (Env::kStaticN && j >= n) break;
       // (the descriptor of the pair (i, i) is zero: an empty window)
-      const bool push = tab_pushes(env, base + j, a, env.x(j) - xi, env.y(j) - yi);
+      const bool push = tab_pushes(env, base + (uint32_t)j, a, env.x(j) - xi, env.y(j) - yi);
       hits |= push ? (1u << j) : 0u;
     }
     hits &= ~pushed;
@@ -84,7 +85,7 @@ PW_HD uint32_t step_tab(Env& env, int action) {
     while (hits) {  // transitive stopping, puzzle.py:376-379
       const int j = pw_ffs(hits) - 1;
       hits &= hits - 1;
-      if (tab_wall(env, nn1, j, a, env.x_dyn(j), env.y_dyn(j))) return 0;
+      if (tab_wall(env, nn1, (uint32_t)j, a, env.x_dyn(j), env.y_dyn(j))) return 0;
     }
   }
   env.translate(pushed, action_dx(action), action_dy(action));

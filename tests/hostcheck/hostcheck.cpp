@@ -20,7 +20,8 @@ struct HostEnv {
   int n_, g_, w_, h_, wall_off_, awall_off_, desc_word_;
   int* px;
   int* py;
-  uint64_t fast(int k) const { return ftab[k]; }
+  uint64_t fast(uint32_t k) const { return ftab[k]; }
+  uint32_t fast32(uint32_t k) const { return reinterpret_cast<const uint32_t*>(ftab)[k]; }
   uint32_t word(int i) const { return reinterpret_cast<const uint32_t*>(base)[i]; }
   void init(const uint64_t* b, int* x, int* y) {
     base = b;
