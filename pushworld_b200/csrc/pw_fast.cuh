@@ -54,11 +54,12 @@ PW_HD bool tab_pushes(const Env& env, uint32_t pair_index, uint32_t a, int rx, i
   return (env.fast32(((uint32_t)pd << 1) + (idx >> 5)) >> (idx & 31u)) & 1u;
 }
 
-// One transition on the tables.  Same contract as step() (pw_core.cuh): returns the moved-object
-// bitmask, 0 if nothing moved.  The scan of a pusher over the other objects is branch-free per
-// object (one pair look-up each); the wall look-ups of the objects it hits come after the scan.
+// The pushed set of one transition, read from the tables: bit k = object k moves (bit 0 = agent),
+// 0 if the action is invalid or anything in the set is stopped.  Positions are not modified.
+// The scan of a pusher over the other objects is branch-free per object (one pair look-up each);
+// the wall look-ups of the objects it hits come after the scan.
 template <class Env>
-PW_HD uint32_t step_tab(Env& env, int action) {
+PW_HD uint32_t pushed_set_tab(const Env& env, int action) {
   if ((unsigned)action > 3u) return 0;  // invalid actions are no-ops (counted by the caller)
   const uint32_t a = (uint32_t)action;
   const int n = env.n();
@@ -88,7 +89,15 @@ PW_HD uint32_t step_tab(Env& env, int action) {
       if (tab_wall(env, nn1, (uint32_t)j, a, env.x_dyn(j), env.y_dyn(j))) return 0;
     }
   }
-  env.translate(pushed, action_dx(action), action_dy(action));
+  return pushed;
+}
+
+// One transition on the tables.  Same contract as step() (pw_core.cuh): returns the moved-object
+// bitmask, 0 if nothing moved.
+template <class Env>
+PW_HD uint32_t step_tab(Env& env, int action) {
+  const uint32_t pushed = pushed_set_tab(env, action);
+  if (pushed) env.translate(pushed, action_dx(action), action_dy(action));
   return pushed;
 }
 

@@ -533,15 +533,31 @@ __global__ void __launch_bounds__(kBlock)
 template <class Env>
 __device__ __forceinline__ void run_expand(Env& env, const ExpandParams& p, int64_t e) {
   env.load(p.x_in, p.y_in, p.stride_in, p.index ? p.index[e] : e);
-  const int g = env.g();
+  const int g = env.g(), n = env.n();
+  const int jend = Env::kStaticN ? Env::kStaticN : n;
 #pragma unroll 1
   for (int a = 0; a < 4; ++a) {
-    const uint32_t moved = step_tab(env, a);
+    // The state itself is never modified: successor a is the state with the pushed set displaced,
+    // written straight to its column (running pointers: one 64-bit add per plane).
+    const uint32_t moved = pushed_set_tab(env, a);
+    const int dx = moved ? action_dx(a) : 0, dy = moved ? action_dy(a) : 0;
     const int64_t s = (int64_t)a * p.N + e;
-    env.store(p.x_out, p.y_out, p.stride_out, s);
+    int32_t* px = p.x_out + s;
+    int32_t* py = p.y_out + s;
+    int at_goal = 0;
+#pragma unroll
+    for (int j = 0; j < jend; ++j) {
+      if (Env::kStaticN && j >= n) break;
+      const bool m = (moved >> j) & 1u;
+      const int x = env.x(j) + (m ? dx : 0), y = env.y(j) + (m ? dy : 0);
+      *px = x;
+      *py = y;
+      px += p.stride_out;
+      py += p.stride_out;
+      if (j >= 1 && j <= g) at_goal += (x == env.goal_x(j - 1) && y == env.goal_y(j - 1)) ? 1 : 0;
+    }
     if (p.moved) p.moved[s] = moved;
-    if (p.goal) p.goal[s] = achieved_goals(env) == g ? 1 : 0;  // pushworld_puzzle.cc:462-469
-    env.translate(moved, -action_dx(a), -action_dy(a));
+    if (p.goal) p.goal[s] = at_goal == g ? 1 : 0;  // pushworld_puzzle.cc:462-469
   }
 }
 
