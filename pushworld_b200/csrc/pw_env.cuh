@@ -22,6 +22,10 @@ namespace pw {
 
 struct SharedTable {
   const uint64_t* base;
+  // the table stored `offset_u64` after `t` (shared memory: plain pointer arithmetic, LDS)
+  static __device__ __forceinline__ SharedTable after(const SharedTable& t, uint32_t offset_u64) {
+    return SharedTable{t.base + offset_u64};
+  }
   __device__ __forceinline__ uint64_t row(int off) const { return base[off]; }
   __device__ __forceinline__ uint64_t qword(uint32_t off) const { return base[off]; }  // unsigned: one IMAD.WIDE
   __device__ __forceinline__ uint32_t dword(uint32_t i) const {
@@ -34,6 +38,14 @@ struct SharedTable {
 
 struct GlobalTable {
   const uint64_t* base;
+  // the table stored `offset_u64` after `t`, as an OPAQUE per-thread pointer: otherwise every
+  // address is rebuilt from the uniform blob pointer plus the puzzle offset (four instructions
+  // instead of one IMAD.WIDE); reads go through __ldg, so the lost address space does not matter
+  static __device__ __forceinline__ GlobalTable after(const GlobalTable& t, uint32_t offset_u64) {
+    const uint64_t* p = t.base + offset_u64;
+    asm volatile("" : "+l"(p));
+    return GlobalTable{p};
+  }
   __device__ __forceinline__ uint64_t row(int off) const { return __ldg(base + off); }
   __device__ __forceinline__ uint64_t qword(uint32_t off) const { return __ldg(base + off); }
   __device__ __forceinline__ uint32_t dword(uint32_t i) const {
@@ -61,11 +73,7 @@ struct EnvBase {
     wall_off_ = (int)t.word(kHdrWallOff);
     awall_off_ = (int)t.word(kHdrAwallOff);
     desc_word_ = (int)t.word(kHdrObjOff) * 2;
-    // an opaque per-thread pointer: otherwise every table address is rebuilt from the uniform blob
-    // pointer plus the puzzle offset (four instructions instead of one IMAD.WIDE)
-    const uint64_t* fast_base = t.base + t.word(kHdrSizeU64);
-    asm volatile("" : "+l"(fast_base));
-    ft = Table{fast_base};
+    ft = Table::after(t, t.word(kHdrSizeU64));
   }
   // points the view at another puzzle's tables (same address space)
   __device__ __forceinline__ void retarget(const uint64_t* base) { init_header(Table{base}); }

@@ -535,30 +535,37 @@ __device__ __forceinline__ void run_expand(Env& env, const ExpandParams& p, int6
   env.load(p.x_in, p.y_in, p.stride_in, p.index ? p.index[e] : e);
   const int g = env.g(), n = env.n();
   const int jend = Env::kStaticN ? Env::kStaticN : n;
+  // The state itself is never modified: successor a is the state with the pushed set displaced,
+  // written straight to its column.  Offset = element index of (object j, successor s); with
+  // 32-bit offsets (every launch whose output planes hold < 2^31 elements) an address is one
+  // IMAD.WIDE on the FMA pipe instead of an add-with-carry pair on the ALU pipe.
+  auto expand = [&](auto first_offset, auto plane_stride) {
+    using Offset = decltype(first_offset);
 #pragma unroll 1
-  for (int a = 0; a < 4; ++a) {
-    // The state itself is never modified: successor a is the state with the pushed set displaced,
-    // written straight to its column (running pointers: one 64-bit add per plane).
-    const uint32_t moved = pushed_set_tab(env, a);
-    const int dx = moved ? action_dx(a) : 0, dy = moved ? action_dy(a) : 0;
-    const int64_t s = (int64_t)a * p.N + e;
-    int32_t* px = p.x_out + s;
-    int32_t* py = p.y_out + s;
-    int at_goal = 0;
+    for (int a = 0; a < 4; ++a) {
+      const uint32_t moved = pushed_set_tab(env, a);
+      const int dx = moved ? action_dx(a) : 0, dy = moved ? action_dy(a) : 0;
+      const Offset s = (Offset)a * (Offset)p.N + first_offset;
+      Offset off = s;
+      int at_goal = 0;
 #pragma unroll
-    for (int j = 0; j < jend; ++j) {
-      if (Env::kStaticN && j >= n) break;
-      const bool m = (moved >> j) & 1u;
-      const int x = env.x(j) + (m ? dx : 0), y = env.y(j) + (m ? dy : 0);
-      *px = x;
-      *py = y;
-      px += p.stride_out;
-      py += p.stride_out;
-      if (j >= 1 && j <= g) at_goal += (x == env.goal_x(j - 1) && y == env.goal_y(j - 1)) ? 1 : 0;
+      for (int j = 0; j < jend; ++j) {
+        if (Env::kStaticN && j >= n) break;
+        const bool m = (moved >> j) & 1u;
+        const int x = env.x(j) + (m ? dx : 0), y = env.y(j) + (m ? dy : 0);
+        p.x_out[off] = x;
+        p.y_out[off] = y;
+        off += plane_stride;
+        if (j >= 1 && j <= g) at_goal += (x == env.goal_x(j - 1) && y == env.goal_y(j - 1)) ? 1 : 0;
+      }
+      if (p.moved) p.moved[s] = moved;
+      if (p.goal) p.goal[s] = at_goal == g ? 1 : 0;  // pushworld_puzzle.cc:462-469
     }
-    if (p.moved) p.moved[s] = moved;
-    if (p.goal) p.goal[s] = at_goal == g ? 1 : 0;  // pushworld_puzzle.cc:462-469
-  }
+  };
+  if (p.stride_out * (int64_t)p.n_max < ((int64_t)1 << 31) && 4 * p.N <= p.stride_out)
+    expand((uint32_t)e, (uint32_t)p.stride_out);
+  else
+    expand((int64_t)e, (int64_t)p.stride_out);
 }
 
 template <int NMAX>
