@@ -30,6 +30,15 @@
 
 namespace pw {
 
+// bit (index & 31) of `word`, as a test against a shifted one (the shift wraps: no masking needed)
+PW_HD bool tab_bit(uint32_t word, uint32_t index) {
+#if defined(__CUDA_ARCH__)
+  return (word & __funnelshift_l(1u, 1u, index)) != 0u;  // 1 << (index & 31): bit 0 wraps around
+#else
+  return ((word >> (index & 31u)) & 1u) != 0u;
+#endif
+}
+
 // `env.fast(k)` = F[k]; `env.fast32(k)` = 32-bit word k of F (little endian: bit b of the bitmap at
 // u64 offset o is bit b & 31 of 32-bit word 2 * o + (b >> 5)).  Is object j at (x, y) stopped by the static cells when moved by action a?
 template <class Env>
@@ -38,7 +47,7 @@ PW_HD bool tab_wall(const Env& env, uint32_t nn1, uint32_t j, uint32_t a, int x,
   const uint32_t hi = (uint32_t)(wd >> 32);
   if ((uint32_t)x > (hi & 63u) || (uint32_t)y > ((hi >> 6) & 0xfffu)) return false;
   const uint32_t idx = (((uint32_t)y * (hi >> 18) + (uint32_t)x) << 2) | a;
-  return (env.fast32(((uint32_t)wd << 1) + (idx >> 5)) >> (idx & 31u)) & 1u;
+  return tab_bit(env.fast32(((uint32_t)wd << 1) + (idx >> 5)), idx);
 }
 
 // Does pusher i (descriptor index base = 1 + i*n), moved by action a, push j at relative position
@@ -51,7 +60,7 @@ PW_HD bool tab_pushes(const Env& env, uint32_t pair_index, uint32_t a, int rx, i
   const uint32_t ux = (uint32_t)(rx + (int)((hi >> 17) & 0x7fu)), uy = (uint32_t)(ry + (int)(hi >> 24));
   if (ux >= Ww || uy >= Hw) return false;
   const uint32_t idx = (a * Hw + uy) * Ww + ux;
-  return (env.fast32(((uint32_t)pd << 1) + (idx >> 5)) >> (idx & 31u)) & 1u;
+  return tab_bit(env.fast32(((uint32_t)pd << 1) + (idx >> 5)), idx);
 }
 
 // The pushed set of one transition, read from the tables: bit k = object k moves (bit 0 = agent),
@@ -72,14 +81,17 @@ PW_HD uint32_t pushed_set_tab(const Env& env, int action) {
     frontier &= frontier - 1;
     const int xi = env.x_dyn(i), yi = env.y_dyn(i);
     const uint32_t base = 1u + (uint32_t)(i * n);
+    // object j's verdict enters at bit 31 and is shifted down once per later object: after the
+    // n - 1 objects, bit 32 - n + j; the final shift by 32 - n puts it at bit j
     uint32_t hits = 0;
 #pragma unroll
     for (int j = 1; j < jend; ++j) {
       if (Env::kStaticN && j >= n) break;
       // (the descriptor of the pair (i, i) is zero: an empty window)
       const bool push = tab_pushes(env, base + (uint32_t)j, a, env.x(j) - xi, env.y(j) - yi);
-      hits |= push ? (1u << j) : 0u;
+      hits = (hits >> 1) | (push ? 0x80000000u : 0u);
     }
+    hits = n > 1 ? hits >> (32 - n) : 0u;
     hits &= ~pushed;
     pushed |= hits;
     frontier |= hits;
