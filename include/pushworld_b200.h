@@ -69,8 +69,10 @@ typedef struct PwEngine PwEngine;
 
 /* ------------------------------------------------------------------------------------
  * Puzzle tables.  A table blob is the compiled, immutable form of one .pwp file: the
- * geometry (row bitmasks) the kernels test directly instead of the reference's
- * precomputed collision hash sets (puzzle.py:259-308).  Layout (little endian, u64
+ * geometry (row bitmasks).  The reference's precomputed collision sets (puzzle.py:259-308)
+ * are not part of the blob: pw_engine_create derives their bitmap equivalent from the
+ * geometry on the host (milliseconds per puzzle) and keeps it on the device next to the
+ * blob (pushworld_b200/csrc/pw_fast.cuh).  Layout (little endian, u64
  * aligned; all offsets in u64 units from the start of the puzzle's blob):
  *
  *   u32 word  0  magic 'PWT1' (0x31545750)
@@ -104,7 +106,8 @@ PW_API int pw_compile_puzzle(const char* text, size_t text_len, void* out, size_
 
 /* Creates an engine on CUDA device `device` from `num_puzzles` concatenated table blobs.
  * offsets_u64[p] = start of puzzle p inside `blob` (u64 units).  `blob` is HOST memory
- * and is copied.  Replaces: constructing PushWorldPuzzle objects (gym_env.py:66-69). */
+ * and is copied; the collision bit tables the kernels read are derived from it here.
+ * Replaces: constructing PushWorldPuzzle objects (gym_env.py:66-69, puzzle.py:259-308). */
 PW_API int pw_engine_create(const void* blob, size_t blob_bytes, const uint32_t* offsets_u64,
                      int num_puzzles, int device, PwEngine** out);
 PW_API int pw_engine_destroy(PwEngine* engine);
