@@ -172,6 +172,47 @@ class Engine:
         )
         return out
 
+    def prepare_step(self, xy: torch.Tensor, puzzle: PuzzleSel, out: Optional[StepOutput] = None,
+                     steps: Optional[torch.Tensor] = None, max_steps: Optional[int] = None,
+                     want_moved: bool = False):
+        """``step`` with everything but the action bound once: returns ``f(action) -> StepOutput``.
+
+        A per-step loop pays for argument checks, tensor views and pointer conversions on every
+        ``step`` call (about 27 us, against 8 us for the kernel); the returned function only checks
+        the action tensor and makes the native call.  ``xy``, ``steps`` and the output tensors must
+        stay alive and unmoved for as long as the function is used."""
+        n = self._chk_state(xy)
+        pid_ptr, pid = self._sel(puzzle, n)
+        if steps is not None:
+            self._chk(steps, torch.int32, (n,), "steps")
+        if out is None:
+            out = StepOutput(
+                reward=torch.empty(n, dtype=torch.float32, device=self.device),
+                dgoals=torch.empty(n, dtype=torch.int8, device=self.device),
+                terminated=torch.empty(n, dtype=torch.uint8, device=self.device),
+                truncated=torch.empty(n, dtype=torch.uint8, device=self.device),
+                moved=torch.empty(n, dtype=torch.int32, device=self.device) if want_moved else None,
+            )
+        keep = (xy, puzzle, steps, out)  # the pointers below must not outlive their tensors
+        fn, handle, device = self._lib.pw_step, self._h, self.device
+        head = (handle, n, pid_ptr, pid, xy[0].data_ptr(), xy[1].data_ptr(), n)
+        tail = (_ptr(out.reward), _ptr(out.dgoals), _ptr(out.terminated), _ptr(out.truncated),
+                _ptr(steps), int(max_steps or 0), _ptr(out.moved))
+        current_stream = torch.cuda.current_stream
+        shape = (n,)
+
+        def run(action: torch.Tensor) -> StepOutput:
+            if (action.dtype is not torch.uint8 or action.device != device or tuple(action.shape) != shape
+                    or not action.is_contiguous()):
+                self._chk(action, torch.uint8, shape, "action")
+            rc = fn(*head, action.data_ptr(), *tail, current_stream(device).cuda_stream)
+            if rc:
+                _lib.check(rc)
+            return out
+
+        run.keep = keep
+        return run
+
     def rollout(self, xy: torch.Tensor, puzzle: PuzzleSel, actions: torch.Tensor,
                 reward: Optional[torch.Tensor] = None, terminated: Optional[torch.Tensor] = None,
                 dgoals: Optional[torch.Tensor] = None, truncated: Optional[torch.Tensor] = None,

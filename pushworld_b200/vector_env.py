@@ -62,6 +62,7 @@ class PushWorldVectorEnv:
         max_steps, border_width, pixels_per_cell, standard_padding: as ``PushWorldEnv``
             (gym_env.py:57-64).
         observation: None (no rendering), "float32" (the reference observation) or "uint8".
+        reuse_step_outputs: ``step`` returns the same output tensors on every call (see ``step``).
     """
 
     def __init__(
@@ -76,6 +77,7 @@ class PushWorldVectorEnv:
         observation: Optional[str] = None,
         device: Union[int, str, torch.device, None] = None,
         autoreset: bool = False,
+        reuse_step_outputs: bool = False,
     ) -> None:
         texts = load_puzzle_texts(puzzles) if isinstance(puzzles, str) else list(puzzles)
         if len(texts) == 0:
@@ -94,6 +96,9 @@ class PushWorldVectorEnv:
         self.pixels_per_cell = pixels_per_cell
         self.observation = observation
         self.autoreset = autoreset
+        # per-step loops: bind the native call's arguments once and write every step's outputs into
+        # the same tensors (Engine.prepare_step: ~2x fewer microseconds per step() call)
+        self.reuse_step_outputs = reuse_step_outputs
 
         max_h, max_w = self.engine.max_height, self.engine.max_width
         if standard_padding:  # gym_env.py:86-105
@@ -174,12 +179,22 @@ class PushWorldVectorEnv:
         return self._observe()
 
     def step(self, actions: torch.Tensor, check_actions: bool = True):
-        """-> (observation or None, reward f32 [N], terminated u8 [N], truncated u8 [N], info)"""
+        """-> (observation or None, reward f32 [N], terminated u8 [N], truncated u8 [N], info)
+
+        With ``reuse_step_outputs=True`` (constructor) and no observations the returned tensors
+        are REUSED by the next ``step`` call (clone them to keep them)."""
         self._require_reset()
         actions = self._as_actions(actions, (self.num_envs,))
-        if self.observation is None:
+        if self.observation is None and not self.reuse_step_outputs:
             out = self.engine.step(self.xy, self._sel, actions, steps=self.steps,
                                    max_steps=self.max_steps)
+            obs = None
+        elif self.observation is None:
+            stepper = getattr(self, "_stepper", None)
+            if stepper is None:  # arguments bound once (Engine.prepare_step); outputs are reused
+                stepper = self._stepper = self.engine.prepare_step(
+                    self.xy, self._sel, steps=self.steps, max_steps=self.max_steps)
+            out = stepper(actions)
             obs = None
         else:
             obs, out = self.engine.step_render(

@@ -105,6 +105,10 @@ def main():
         ms = time_ms(lambda: eng.step(xy, 0, act, out=out))
         results.append(report("cfg2 single step (pw_step): Road Block 2^18", n, ms, 16 * 3 + 6,
                               {"unit": "env-steps", "note": "one Python call per step: launch-bound"}))
+        stepper = eng.prepare_step(xy, 0, out=out)
+        ms = time_ms(lambda: stepper(act))
+        results.append(report("cfg2 single step through Engine.prepare_step: Road Block 2^18", n, ms, 16 * 3 + 6,
+                              {"unit": "env-steps", "note": "arguments bound once; still one launch per Python call"}))
         # the kernel itself: 50 steps captured in one CUDA graph (no host work between the launches)
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream())
