@@ -22,6 +22,8 @@ namespace {
 
 #define COMMA ,
 constexpr int kBlock = 128;
+// most shared memory a uniform-puzzle launch may use for its staged tables (+ state arrays)
+constexpr size_t kStageLimit = 160 * 1024;
 
 // Copies one puzzle blob into shared memory (all threads of the block take part).
 __device__ __forceinline__ void stage_table(uint64_t* dst, const uint64_t* src, int n_u64) {
@@ -479,7 +481,7 @@ __global__ void __launch_bounds__(kBlock, MIN_BLOCKS)
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   StepCounts c;
   if (e < p.N) {
-    const int pid = p.puzzle_id[e];
+    const int pid = p.puzzle_id ? p.puzzle_id[e] : p.puzzle_uniform;
     const GlobalTable tbl{p.blob + p.puzzle_off[pid]};
     Board<NMAX, Word> s;
     BoardSimMixed<NMAX, Word> sim{s, nullptr, 0u, 0};
@@ -512,7 +514,7 @@ __global__ void __launch_bounds__(kBlock)
   __syncthreads();
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool active = e < p.N;
-  const int pid = active ? p.puzzle_id[e] : 0;
+  const int pid = (active && p.puzzle_id) ? p.puzzle_id[e] : p.puzzle_uniform;
   const GlobalTable table{p.blob + p.puzzle_off[pid]};
   if constexpr (NMAX > 0) {
     RegEnv<NMAX, GlobalTable> env;
@@ -592,7 +594,7 @@ __global__ void __launch_bounds__(kBlock) k_expand_mixed(const ExpandParams p) {
   extern __shared__ uint64_t smem[];
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= p.N) return;
-  const GlobalTable table{p.blob + p.puzzle_off[p.puzzle_id[e]]};
+  const GlobalTable table{p.blob + p.puzzle_off[p.puzzle_id ? p.puzzle_id[e] : p.puzzle_uniform]};
   if constexpr (NMAX > 0) {
     RegEnv<NMAX, GlobalTable> env;
     env.init(table);
@@ -810,8 +812,10 @@ cudaError_t launch_steps(const StepParams& p, int n_limit, cudaStream_t stream) 
     else                                                                  \
       kernel, false><<<grid, kBlock, smem_bytes, stream>>>(p);            \
   } while (0)
-  if (p.puzzle_id == nullptr) {
-    const size_t tbl = (size_t)p.uniform_u64 * 8;
+  // a single puzzle whose tables fit in shared memory is staged there; a larger one is read
+  // through the global-table kernels like a mixed batch
+  const size_t tbl = (size_t)p.uniform_u64 * 8;
+  if (p.puzzle_id == nullptr && tbl + (n_limit > 8 ? state_bytes : 0) <= kStageLimit) {
     if (p.board_bits <= 64 && n_limit <= 8) {
       // bitboard kernels: uint32 / uint64 boards; lean rollouts get exact-n instantiations
       const bool w32 = p.board_bits <= 32;
@@ -884,8 +888,8 @@ cudaError_t launch_expand(const ExpandParams& p, int n_limit, cudaStream_t strea
   if (p.N == 0) return cudaSuccess;
   const unsigned grid = grid_for(p.N);
   const size_t state_bytes = (size_t)p.n_max * 2 * kBlock * sizeof(int);
-  if (p.puzzle_id == nullptr) {
-    const size_t tbl = (size_t)p.uniform_u64 * 8;
+  const size_t tbl = (size_t)p.uniform_u64 * 8;
+  if (p.puzzle_id == nullptr && tbl + (n_limit > 8 ? state_bytes : 0) <= kStageLimit) {
     if (n_limit <= 4) {
       k_expand_uniform<4><<<grid, kBlock, tbl, stream>>>(p);
     } else if (n_limit <= 8) {
@@ -931,13 +935,20 @@ cudaError_t launch_novelty(const NoveltyParams& p, cudaStream_t stream) {
 }
 
 cudaError_t configure_kernels(size_t max_dynamic_smem) {
-  // dynamic shared memory above 48 KB needs an explicit opt-in per kernel
+  // dynamic shared memory above 48 KB needs an explicit opt-in per kernel; a puzzle whose tables
+  // do not fit the limit is read through the global-table kernels instead (launch_steps /
+  // launch_expand), so the request is capped rather than refused
+  if (max_dynamic_smem > kStageLimit) max_dynamic_smem = kStageLimit;
   cudaError_t err = cudaSuccess;
 #define PW_OPT_IN(k)                                                                             \
   if (err == cudaSuccess)                                                                        \
   err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_dynamic_smem)
   PW_OPT_IN((k_steps_uniform<0, true>));
   PW_OPT_IN((k_steps_uniform<0, false>));
+  PW_OPT_IN((k_steps_uniform<4, true>));
+  PW_OPT_IN((k_steps_uniform<4, false>));
+  PW_OPT_IN((k_steps_uniform<8, true>));
+  PW_OPT_IN((k_steps_uniform<8, false>));
   PW_OPT_IN((k_steps_mixed<0, true>));
   PW_OPT_IN((k_steps_mixed<0, false>));
   PW_OPT_IN(k_expand_uniform<0>);

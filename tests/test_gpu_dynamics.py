@@ -529,3 +529,52 @@ def test_ring_rollout_kernel_matches_oracle(golden):
             assert counters.cpu().numpy().tolist() == [n * T, n_term, n_moved, n_gain], (text, T)
             assert engine.poll_invalid_actions() == int((actions > 3).sum())
     assert len(seen_n) >= 5 and len(seen_g) >= 2 and max_bits >= 27, (seen_n, seen_g, max_bits)
+
+
+def test_puzzle_whose_tables_exceed_shared_memory():
+    """A 60 x 1000 puzzle: its collision bit tables (~190 KB) do not fit the shared-memory staging
+    limit, so single-puzzle launches read them through the global-table kernels.  Rollout, step and
+    expansion against the oracle."""
+    from pushworld_b200.engine import Engine
+
+    rng = np.random.default_rng(99)
+    w, h = 60, 1000
+    grid = [["." for _ in range(w)] for _ in range(h)]
+    grid[500][30] = "a"
+    grid[499][30] = "a"
+    for k, (x, y) in enumerate([(31, 500), (29, 500), (30, 498), (30, 501), (32, 500)]):
+        grid[y][x] = f"m{k}"
+    grid[500][34] = "w"
+    grid[496][30] = "aw"
+    grid[503][30] = "g0"
+    text = "\n".join(" ".join(row) for row in grid) + "\n"
+    oracle = po.OraclePuzzle(text)
+    engine = Engine([text])
+    n, T = 64, 60
+    actions = rng.integers(0, 4, size=(T, n)).astype(np.uint8)
+    xy = engine.new_state(n)
+    engine.reset(xy, 0)
+    reward = torch.empty((T, n), dtype=torch.float32, device="cuda")
+    term = torch.empty((T, n), dtype=torch.uint8, device="cuda")
+    engine.rollout(xy, 0, torch.from_numpy(actions).cuda(), reward=reward, terminated=term)
+    final, r, te = xy.cpu().numpy(), reward.cpu().numpy(), term.cpu().numpy()
+    states = []
+    for e in range(n):
+        st = oracle.initial_state
+        for t in range(T):
+            nxt = oracle.get_next_state(st, int(actions[t, e]))
+            rr, tt, _ = po.step_reward(oracle, st, nxt)
+            assert np.float32(rr) == r[t, e] and tt == bool(te[t, e]), (e, t)
+            st = nxt
+        got = tuple((int(final[0, j, e]), int(final[1, j, e])) for j in range(oracle.num_objects))
+        assert got == st, e
+        states.append(st)
+    xy_out, moved, goal = engine.expand(xy, 0)
+    xo, mo, go = xy_out.cpu().numpy(), moved.cpu().numpy(), goal.cpu().numpy()
+    for e in range(n):
+        for a in range(4):
+            nxt, moved_idx = oracle.get_next_state_and_moved(states[e], a)
+            s = a * n + e
+            got = tuple((int(xo[0, j, s]), int(xo[1, j, s])) for j in range(oracle.num_objects))
+            assert got == nxt and int(mo[s]) == sum(1 << k for k in moved_idx), (e, a)
+            assert bool(go[s]) == oracle.is_goal_state(nxt)
