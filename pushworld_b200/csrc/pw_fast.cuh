@@ -75,6 +75,12 @@ PW_HD uint32_t pushed_set_tab(const Env& env, int action) {
   const uint32_t nn1 = 1u + (uint32_t)(n * n);
   if (tab_wall(env, nn1, 0u, a, env.x(0), env.y(0))) return 0;  // puzzle.py:353-354
   const int jend = Env::kStaticN ? Env::kStaticN : n;
+#ifndef PW_SCAN_UNROLL
+#define PW_SCAN_UNROLL 4
+#endif
+  // register policies unroll the scan completely; the shared-memory policy keeps several objects'
+  // independent look-up chains in flight per iteration
+  constexpr int kUnroll = Env::kStaticN ? Env::kStaticN : PW_SCAN_UNROLL;
   uint32_t pushed = 1u, frontier = 1u;
   while (frontier) {
     const int i = pw_ffs(frontier) - 1;
@@ -84,7 +90,7 @@ PW_HD uint32_t pushed_set_tab(const Env& env, int action) {
     // object j's verdict enters at bit 31 and is shifted down once per later object: after the
     // n - 1 objects, bit 32 - n + j; the final shift by 32 - n puts it at bit j
     uint32_t hits = 0;
-#pragma unroll
+#pragma unroll kUnroll
     for (int j = 1; j < jend; ++j) {
       if (Env::kStaticN && j >= n) break;
       // (the descriptor of the pair (i, i) is zero: an empty window)
