@@ -83,6 +83,11 @@ __global__ void __launch_bounds__(1024) k(uint32_t* out, uint32_t seed, long lon
                    : "+r"(x[0]), "+r"(x[1]), "+r"(x[2]), "+r"(x[3]), "+r"(x[4]), "+r"(x[5]), "+r"(x[6]), "+r"(x[7])
                    : "r"(y), "r"(z));
       y += 1;
+    } else if (KIND == 12) {  // IMAD.WIDE.U32 (64-bit product of two 32-bit values), halves folded by a LOP3
+      unsigned long long w;
+#define OP(i) asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(w) : "r"(x[i]), "r"(y)); x[i] = (uint32_t)w ^ (uint32_t)(w >> 32);
+      CHAINS8(OP)
+#undef OP
     }
   }
   const long long t1 = clock64();
@@ -122,6 +127,7 @@ int main() {
   run<11>("SEL x4 + LOP3 x4 (+ISETP, IADD)", 10 + 3);
   run<9>("PLOP3 x8 (+2 ISETP, SEL, IADD)", 12 + 3);
   run<10>("LOP3->P x6 + SEL x6 (+IADD)", 13 + 3);
+  run<12>("(IMAD.WIDE, LOP3) x8", 16 + 3);
   run<1>("(LOP3->P, SEL) x8", 16 + 3);
   run<5>("(2 LOP3->P, PLOP3, SEL) x8", 32 + 3);
   return 0;
