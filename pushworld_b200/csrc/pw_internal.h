@@ -29,6 +29,7 @@ struct StepParams {
   int32_t n_max;        // planes in x / y
   int32_t board_bits;   // bits puzzle_uniform needs in board form if it is regular, else 1 << 30
   int32_t ring_goals;   // > 0: puzzle_uniform fits ring boards (pw_board.cuh), value = its goal count
+  int32_t lean_tiles;   // set by launch_steps: lean shape, N % 32 == 0, 16-byte aligned actions
   const BoardStaticPod* board_static;  // device; entry of puzzle_uniform (valid if board_bits <= 64)
   int32_t* x;
   int32_t* y;

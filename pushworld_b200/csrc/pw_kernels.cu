@@ -465,6 +465,95 @@ struct BoardSimMixed {
   __device__ __forceinline__ int goals() const { return s.g; }
 };
 
+// ------------------------------------------------------------------------------------------
+// The plain-rollout loop of the ring kernel for boards in general (edge-mask rule, uint32 or
+// uint64, any goal count, per-thread puzzles): same action tiles (cp.async, 32 steps ahead), same
+// half-offset addressing, same block-level action check; the rule itself is board_step.
+// `acts` points at this thread's per-action constants in shared memory, action a at acts[a * kBlock].
+// ------------------------------------------------------------------------------------------
+template <int NMAX, typename Word>
+__device__ __forceinline__ void run_board_lean(Board<NMAX, Word>& s, const StepParams& p, const int64_t e,
+                                               const float* s_rlut, uint8_t* tiles,
+                                               const BoardAction<Word>* acts, StepCounts& c) {
+  const int g = s.g;
+  const int T = p.T;
+  const uint32_t half_n = (uint32_t)(p.N >> 1);
+  uint8_t* term_base = p.terminated + (e & 1);
+  float* const reward_base = p.reward + (e & 1);
+  asm volatile("" : "+l"(term_base));  // see run_ring_lean
+  uint32_t h_out = (uint32_t)(e >> 1);
+  int prev = board_achieved(s);
+  uint32_t n_term = 0, n_moved = 0, n_gain = 0, n_invalid = 0;
+  auto one_step = [&](const uint32_t a, auto checked) {
+    constexpr bool kChecked = decltype(checked)::value;
+    const uint32_t moved = board_step(s, (int)a, acts[(kChecked ? (a & 3u) : a) * kBlock]);
+    const int ach = board_achieved(s);
+    const bool term = ach == g;  // puzzle.py:409-411
+    const int dg = ach - prev;
+    prev = ach;
+    // gym_env.py:212-221; the float64 value (dg - 0.01) was rounded to float32 once, on the host
+    const float r = term ? 10.0f : s_rlut[dg + kMaxObjects];
+    const uint32_t tbyte = term ? 1u : 0u;
+    n_term += tbyte;
+    n_moved += moved ? 1u : 0u;
+    n_gain += (uint32_t)max(dg, 0);
+    if (kChecked) n_invalid += a > 3u ? 1u : 0u;
+    reward_base[(size_t)h_out * 2u] = r;
+    asm volatile("st.global.u8 [%0], %1;" ::"l"(term_base + (size_t)h_out * 2u), "r"(tbyte) : "memory");
+    h_out += half_n;
+  };
+  constexpr int kBlockSteps = 32, kGroup = 4;
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint8_t* const warp_actions = p.actions + (e - (int64_t)lane);
+  const uint32_t tiles_s = (uint32_t)__cvta_generic_to_shared(tiles);
+  auto issue_block = [&](const int block) {
+    const int row = block * kBlockSteps + (int)lane;
+    const uint8_t* src = warp_actions + (size_t)(row < T ? row : T - 1) * (size_t)p.N;  // clamped: never used
+    const uint32_t dst = tiles_s + (uint32_t)(block & 1) * 1024u + lane * 32u;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u), "l"(src + 16) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  const int blocks = (T + kBlockSteps - 1) / kBlockSteps;
+  issue_block(0);
+  for (int blk = 0; blk < blocks; ++blk) {
+    __syncwarp();
+    issue_block(blk + 1);
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+    __syncwarp();
+    const uint8_t* tile = tiles + (blk & 1) * 1024;
+    const uint4 w0 = *reinterpret_cast<const uint4*>(tile + lane * 32u);
+    const uint4 w1 = *reinterpret_cast<const uint4*>(tile + lane * 32u + 16u);
+    const uint32_t seen = w0.x | w0.y | w0.z | w0.w | w1.x | w1.y | w1.z | w1.w;
+    const bool any_invalid = __any_sync(0xffffffffu, (seen & 0xfcfcfcfcu) != 0u);
+    const int steps = T - blk * kBlockSteps < kBlockSteps ? T - blk * kBlockSteps : kBlockSteps;
+    const uint8_t* mine = tile + lane;
+    if (!any_invalid && steps == kBlockSteps) {
+#pragma unroll 1
+      for (int gi = 0; gi < kBlockSteps / kGroup; ++gi, mine += kGroup * 32) {
+#pragma unroll
+        for (int k = 0; k < kGroup; ++k) one_step(mine[k * 32], std::false_type{});
+      }
+    } else {
+#pragma unroll 1
+      for (int k = 0; k < steps; ++k, mine += 32) one_step(mine[0], std::true_type{});
+    }
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  c.terminated += n_term;
+  c.moved += n_moved;
+  c.dgoals += n_gain;
+  c.invalid += n_invalid;
+#pragma unroll
+  for (int k = 0; k < NMAX; ++k)
+    if (k < s.n) {
+      int x, y;
+      board_position<Word>(s.b[k], s.P, &x, &y);
+      p.x[k * p.stride + e] = x;
+      p.y[k * p.stride + e] = y;
+    }
+}
+
 __device__ __noinline__ void general_slow_path_global(const uint64_t* table, const StepParams& p,
                                                       int64_t e, StepCounts& c) {
   LocalEnv<GlobalTable> env;
@@ -476,6 +565,13 @@ template <int NMAX, typename Word, int MIN_BLOCKS, bool kLean>
 __global__ void __launch_bounds__(kBlock, MIN_BLOCKS)
     k_steps_board_mixed(const __grid_constant__ StepParams p) {
   __shared__ uint32_t s_counters[4];
+  // lean launches only (see run_board_lean): per-warp action tiles, per-thread action constants and a
+  // shared-memory copy of the reward table
+  __shared__ __align__(16) uint8_t s_tiles[kLean ? kBlock / 32 : 1][2][kLean ? 32 * 32 : 16];
+  __shared__ BoardAction<Word> s_act[kLean ? 4 : 1][kLean ? kBlock : 1];
+  __shared__ float s_rlut[kLean ? 2 * kMaxObjects + 1 : 1];
+  if (kLean)
+    for (int i = threadIdx.x; i < 2 * kMaxObjects + 1; i += blockDim.x) s_rlut[i] = c_reward_lut[i];
   if (threadIdx.x < 4) s_counters[threadIdx.x] = 0;
   __syncthreads();
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -489,7 +585,17 @@ __global__ void __launch_bounds__(kBlock, MIN_BLOCKS)
     const bool regular = board_load(s, tbl, [&](int k) { return p.x[k * p.stride + e]; },
                                     [&](int k) { return p.y[k * p.stride + e]; });
     // episode handling re-points the thread at other puzzles: stay on boards (all eligible)
-    if (regular) {
+    if (kLean && p.lean_tiles) {
+      // plain rollout with whole warps (N % 32 == 0): action tiles + FMA-pipe addressing; a warp
+      // with any irregular state takes the general rule for all its lanes
+      if (__all_sync(0xffffffffu, regular)) {
+#pragma unroll
+        for (int a = 0; a < 4; ++a) s_act[a][threadIdx.x] = board_action_of(s, (uint32_t)a);
+        run_board_lean<NMAX, Word>(s, p, e, s_rlut, s_tiles[threadIdx.x >> 5][0], &s_act[0][threadIdx.x], c);
+      } else {
+        general_slow_path_global(tbl.base, p, e, c);
+      }
+    } else if (regular) {
       run_steps_sim<kLean>(sim, p, e, c);
     } else if (!(p.flags & kFlagResample)) {
       general_slow_path_global(tbl.base, p, e, c);
@@ -776,8 +882,11 @@ inline unsigned grid_for(int64_t n) { return (unsigned)((n + kBlock - 1) / kBloc
 // ------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------
-cudaError_t launch_steps(const StepParams& p, int n_limit, cudaStream_t stream) {
-  if (p.N == 0 || p.T == 0) return cudaSuccess;
+cudaError_t launch_steps(const StepParams& p_in, int n_limit, cudaStream_t stream) {
+  if (p_in.N == 0 || p_in.T == 0) return cudaSuccess;
+  StepParams p = p_in;
+  // lean launches made of whole warps with 16-byte aligned actions can stage actions with cp.async
+  p.lean_tiles = is_lean(p) && (p.N & 31) == 0 && (reinterpret_cast<uintptr_t>(p.actions) & 15u) == 0;
   const unsigned grid = grid_for(p.N);
   const size_t state_bytes = (size_t)p.n_max * 2 * kBlock * sizeof(int);
   const bool lean = is_lean(p);
@@ -826,8 +935,7 @@ cudaError_t launch_steps(const StepParams& p, int n_limit, cudaStream_t stream) 
     else                                                                                        \
       k_steps_board<NB, uint64_t, MINB, true><<<grid, kBlock, tbl, stream>>>(p);                \
   } while (0)
-      if (lean && p.ring_goals > 0 && n_limit >= 2 && (p.N & 31) == 0 &&
-          (reinterpret_cast<uintptr_t>(p.actions) & 15u) == 0) {
+      if (p.lean_tiles && p.ring_goals > 0 && n_limit >= 2) {
         // ring boards: one rotate per object, guard zone instead of edge rows
 #define PW_RING(NB, MINB)                                                                       \
   do {                                                                                          \
