@@ -175,12 +175,23 @@ __device__ __noinline__ void general_slow_path(const uint64_t* table, const Step
   run_steps_thread<false>(env, p, e, c);
 }
 
+template <int NMAX, typename Word>
+__device__ __forceinline__ void run_board_lean(Board<NMAX, Word>& s, const StepParams& p, const int64_t e,
+                                               const float* s_rlut, uint8_t* tiles,
+                                               const BoardAction<Word>* acts, StepCounts& c);
+
 template <int NMAX, typename Word, int MIN_BLOCKS, bool kLean>
 __global__ void __launch_bounds__(kBlock, MIN_BLOCKS)
     k_steps_board(const __grid_constant__ StepParams p) {
   extern __shared__ uint64_t smem[];
   __shared__ uint32_t s_counters[4];
   __shared__ BoardStatic<Word> st;
+  // lean launches only (see run_board_lean)
+  __shared__ __align__(16) uint8_t s_tiles[kLean ? kBlock / 32 : 1][2][kLean ? 32 * 32 : 16];
+  __shared__ BoardAction<Word> s_act[kLean ? 4 : 1][kLean ? kBlock : 1];
+  __shared__ float s_rlut[kLean ? 2 * kMaxObjects + 1 : 1];
+  if (kLean)
+    for (int i = threadIdx.x; i < 2 * kMaxObjects + 1; i += blockDim.x) s_rlut[i] = c_reward_lut[i];
   if (threadIdx.x < 4) s_counters[threadIdx.x] = 0;
   const SharedTable tbl{smem};
   // static boards were computed on the host at engine creation (pw_abi.cu: make_board_static)
@@ -219,7 +230,16 @@ __global__ void __launch_bounds__(kBlock, MIN_BLOCKS)
     for (int k = 0; k < NMAX; ++k) s.goal[k] = st.goal[k];
     const bool regular = board_load(s, tbl, [&](int k) { return p.x[k * p.stride + e]; },
                                     [&](int k) { return p.y[k * p.stride + e]; });
-    if (regular) {
+    if (kLean && p.lean_tiles) {
+      // plain rollout with whole warps: the action tiles / addressing of the ring kernel (run_board_lean)
+      if (__all_sync(0xffffffffu, regular)) {
+#pragma unroll
+        for (int a = 0; a < 4; ++a) s_act[a][threadIdx.x] = st.act[a];
+        run_board_lean<NMAX, Word>(s, p, e, s_rlut, s_tiles[threadIdx.x >> 5][0], &s_act[0][threadIdx.x], c);
+      } else {
+        general_slow_path(smem, p, e, c);
+      }
+    } else if (regular) {
       BoardSim<NMAX, Word> sim{s, st, 0u, 0};
       run_steps_sim<kLean>(sim, p, e, c);
     } else {

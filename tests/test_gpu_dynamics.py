@@ -578,3 +578,60 @@ def test_puzzle_whose_tables_exceed_shared_memory():
             got = tuple((int(xo[0, j, s]), int(xo[1, j, s])) for j in range(oracle.num_objects))
             assert got == nxt and int(mo[s]) == sum(1 << k for k in moved_idx), (e, a)
             assert bool(go[s]) == oracle.is_goal_state(nxt)
+
+
+def test_plain_rollouts_on_non_ring_board_puzzles(golden):
+    """Plain rollouts (reward + terminated) of single puzzles that fit one machine word but not the
+    ring condition run k_steps_board with the action tiles of run_board_lean (uint32 and uint64
+    boards): against the oracle, with invalid actions, odd step counts and irregular start states."""
+    from pushworld_b200.engine import Engine
+
+    rng = np.random.default_rng(808)
+    picked = []
+    for key in golden.keys():
+        if not key.startswith("benchmark/"):
+            continue
+        rec = golden.rec(key)
+        bits = 1 + (rec["height"] - 2) * (rec["width"] - 1)
+        if bits <= 64 and bits + rec["width"] - 1 > 32 and rec["n"] <= 8:
+            picked.append((bits, key))
+    picked.sort()
+    assert len(picked) >= 6 and picked[0][0] <= 32 < picked[-1][0], picked  # both word sizes
+    for bits, key in picked[:3] + picked[-3:]:
+        text = golden.text(key)
+        oracle = po.OraclePuzzle(text)
+        engine = Engine([text])
+        n = 64
+        states = []
+        for e in range(n):
+            st = oracle.initial_state
+            for _ in range(int(rng.integers(0, 25))):
+                st = oracle.get_next_state(st, int(rng.integers(4)))
+            if e % 13 == 7 and oracle.num_objects >= 3:  # irregular: object 2 dropped onto object 1
+                st = st[:2] + (st[1],) + st[3:]
+            states.append(st)
+        for T in (5, 32, 71):
+            actions = rng.integers(0, 5, size=(T, n)).astype(np.uint8)  # 4 = invalid -> no-op
+            xy = engine.state_from_tuples(states)
+            reward = torch.empty((T, n), dtype=torch.float32, device="cuda")
+            term = torch.empty((T, n), dtype=torch.uint8, device="cuda")
+            counters = torch.zeros(4, dtype=torch.int64, device="cuda")
+            engine.rollout(xy, 0, torch.from_numpy(actions).cuda(), reward=reward, terminated=term,
+                           counters=counters)
+            final, r, te = xy.cpu().numpy(), reward.cpu().numpy(), term.cpu().numpy()
+            n_term = n_moved = n_gain = 0
+            for e in range(n):
+                st = states[e]
+                for t in range(T):
+                    a = int(actions[t, e])
+                    nxt = st if a > 3 else oracle.get_next_state(st, a)
+                    rr, tt, _ = po.step_reward(oracle, st, nxt)
+                    assert np.float32(rr) == r[t, e] and tt == bool(te[t, e]), (key, T, e, t)
+                    n_term += tt
+                    n_moved += nxt != st
+                    n_gain += max(oracle.count_achieved_goals(nxt) - oracle.count_achieved_goals(st), 0)
+                    st = nxt
+                got = tuple((int(final[0, j, e]), int(final[1, j, e])) for j in range(oracle.num_objects))
+                assert got == st, (key, T, e)
+            assert counters.cpu().numpy().tolist() == [n * T, n_term, n_moved, n_gain], (key, T)
+            assert engine.poll_invalid_actions() == int((actions > 3).sum())
