@@ -70,11 +70,34 @@ __device__ __forceinline__ void flush_counts(const StepCounts& c, const StepPara
   }
 }
 
+template <class Sim>
+__device__ __forceinline__ void run_lean_sim(Sim& sim, const StepParams& p, const int64_t e,
+                                             const float* s_rlut, uint8_t* tiles, StepCounts& c);
+template <class Env>
+struct GeneralLeanSim;
+
 template <bool kLean, class Env>
 __device__ __forceinline__ void run_steps(Env& env, const StepParams& p, int64_t e, bool active,
                                           uint32_t* s_counters) {
   StepCounts c;
-  if (active) run_steps_thread<kLean>(env, p, e, c);
+  if constexpr (kLean) {
+    // plain rollouts made of whole warps: action tiles + FMA-pipe addressing (run_lean_sim)
+    __shared__ __align__(16) uint8_t s_tiles[kBlock / 32][2][32 * 32];
+    __shared__ float s_rlut[2 * kMaxObjects + 1];
+    if (p.lean_tiles) {
+      for (int i = threadIdx.x; i < 2 * kMaxObjects + 1; i += blockDim.x) s_rlut[i] = c_reward_lut[i];
+      __syncthreads();
+      if (active) {
+        env.load(p.x, p.y, p.stride, e);
+        GeneralLeanSim<Env> sim{env};
+        run_lean_sim(sim, p, e, s_rlut, s_tiles[threadIdx.x >> 5][0], c);
+      }
+    } else if (active) {
+      run_steps_thread<kLean>(env, p, e, c);
+    }
+  } else {
+    if (active) run_steps_thread<kLean>(env, p, e, c);
+  }
   flush_counts(c, p, s_counters);
 }
 
@@ -486,28 +509,27 @@ struct BoardSimMixed {
 };
 
 // ------------------------------------------------------------------------------------------
-// The plain-rollout loop of the ring kernel for boards in general (edge-mask rule, uint32 or
-// uint64, any goal count, per-thread puzzles): same action tiles (cp.async, 32 steps ahead), same
-// half-offset addressing, same block-level action check; the rule itself is board_step.
-// `acts` points at this thread's per-action constants in shared memory, action a at acts[a * kBlock].
+// The plain-rollout loop of the ring kernel for every other rule: same action tiles (cp.async, 32
+// steps ahead), same half-offset addressing, same block-level action check.  `Sim` supplies the
+// rule: do_step<kChecked>(a) -> moved mask, achieved(), goals(), store(), kCheapAchieved.
+// Whole warps only (the launcher sets p.lean_tiles when N % 32 == 0 and actions are 16-byte aligned).
 // ------------------------------------------------------------------------------------------
-template <int NMAX, typename Word>
-__device__ __forceinline__ void run_board_lean(Board<NMAX, Word>& s, const StepParams& p, const int64_t e,
-                                               const float* s_rlut, uint8_t* tiles,
-                                               const BoardAction<Word>* acts, StepCounts& c) {
-  const int g = s.g;
+template <class Sim>
+__device__ __forceinline__ void run_lean_sim(Sim& sim, const StepParams& p, const int64_t e,
+                                             const float* s_rlut, uint8_t* tiles, StepCounts& c) {
+  const int g = sim.goals();
   const int T = p.T;
   const uint32_t half_n = (uint32_t)(p.N >> 1);
   uint8_t* term_base = p.terminated + (e & 1);
   float* const reward_base = p.reward + (e & 1);
   asm volatile("" : "+l"(term_base));  // see run_ring_lean
   uint32_t h_out = (uint32_t)(e >> 1);
-  int prev = board_achieved(s);
+  int prev = sim.achieved();
   uint32_t n_term = 0, n_moved = 0, n_gain = 0, n_invalid = 0;
   auto one_step = [&](const uint32_t a, auto checked) {
     constexpr bool kChecked = decltype(checked)::value;
-    const uint32_t moved = board_step(s, (int)a, acts[(kChecked ? (a & 3u) : a) * kBlock]);
-    const int ach = board_achieved(s);
+    const uint32_t moved = sim.template do_step<kChecked>(a);
+    const int ach = Sim::kCheapAchieved ? sim.achieved() : (moved ? sim.achieved() : prev);
     const bool term = ach == g;  // puzzle.py:409-411
     const int dg = ach - prev;
     prev = ach;
@@ -522,7 +544,7 @@ __device__ __forceinline__ void run_board_lean(Board<NMAX, Word>& s, const StepP
     asm volatile("st.global.u8 [%0], %1;" ::"l"(term_base + (size_t)h_out * 2u), "r"(tbyte) : "memory");
     h_out += half_n;
   };
-  constexpr int kBlockSteps = 32, kGroup = 4;
+  constexpr int kBlockSteps = 32, kGroup = Sim::kGroup;
   const uint32_t lane = threadIdx.x & 31u;
   const uint8_t* const warp_actions = p.actions + (e - (int64_t)lane);
   const uint32_t tiles_s = (uint32_t)__cvta_generic_to_shared(tiles);
@@ -564,15 +586,55 @@ __device__ __forceinline__ void run_board_lean(Board<NMAX, Word>& s, const StepP
   c.moved += n_moved;
   c.dgoals += n_gain;
   c.invalid += n_invalid;
-#pragma unroll
-  for (int k = 0; k < NMAX; ++k)
-    if (k < s.n) {
-      int x, y;
-      board_position<Word>(s.b[k], s.P, &x, &y);
-      p.x[k * p.stride + e] = x;
-      p.y[k * p.stride + e] = y;
-    }
+  sim.store(p, e);
 }
+
+// boards with the edge-mask rule; `acts` = this thread's per-action constants in shared memory,
+// action a at acts[a * kBlock]
+template <int NMAX, typename Word>
+struct BoardLeanSim {
+  static constexpr bool kCheapAchieved = true;
+  static constexpr int kGroup = 4;
+  Board<NMAX, Word>& s;
+  const BoardAction<Word>* acts;
+  template <bool kChecked>
+  __device__ __forceinline__ uint32_t do_step(uint32_t a) {
+    return board_step(s, (int)a, acts[(kChecked ? (a & 3u) : a) * kBlock]);
+  }
+  __device__ __forceinline__ int achieved() const { return board_achieved(s); }
+  __device__ __forceinline__ int goals() const { return s.g; }
+  __device__ __forceinline__ void store(const StepParams& p, int64_t e) {
+#pragma unroll
+    for (int k = 0; k < NMAX; ++k)
+      if (k < s.n) {
+        int x, y;
+        board_position<Word>(s.b[k], s.P, &x, &y);
+        p.x[k * p.stride + e] = x;
+        p.y[k * p.stride + e] = y;
+      }
+  }
+};
+
+template <int NMAX, typename Word>
+__device__ __forceinline__ void run_board_lean(Board<NMAX, Word>& s, const StepParams& p, const int64_t e,
+                                               const float* s_rlut, uint8_t* tiles,
+                                               const BoardAction<Word>* acts, StepCounts& c) {
+  BoardLeanSim<NMAX, Word> sim{s, acts};
+  run_lean_sim(sim, p, e, s_rlut, tiles, c);
+}
+
+// the general rule (collision bit tables) on an Env policy; the (large) rule is not unrolled
+template <class Env>
+struct GeneralLeanSim {
+  static constexpr bool kCheapAchieved = false;
+  static constexpr int kGroup = 1;
+  Env& env;
+  template <bool kChecked>
+  __device__ __forceinline__ uint32_t do_step(uint32_t a) { return step_tab(env, (int)a); }
+  __device__ __forceinline__ int achieved() const { return achieved_goals(env); }
+  __device__ __forceinline__ int goals() const { return env.g(); }
+  __device__ __forceinline__ void store(const StepParams& p, int64_t e) { env.store(p.x, p.y, p.stride, e); }
+};
 
 __device__ __noinline__ void general_slow_path_global(const uint64_t* table, const StepParams& p,
                                                       int64_t e, StepCounts& c) {

@@ -635,3 +635,51 @@ def test_plain_rollouts_on_non_ring_board_puzzles(golden):
                 assert got == st, (key, T, e)
             assert counters.cpu().numpy().tolist() == [n * T, n_term, n_moved, n_gain], (key, T)
             assert engine.poll_invalid_actions() == int((actions > 3).sum())
+
+
+def test_plain_rollouts_on_the_general_rule(setup, golden):
+    """Plain rollouts (reward + terminated only, whole warps) take run_lean_sim with the table rule:
+    the golden walks of all 223 benchmark puzzles in one mixed launch (224 environments), and
+    single-puzzle launches of a few large puzzles (shared-memory tables), step by step against the
+    reference's recorded trajectories."""
+    engine, keys = setup
+    bench = [k for k in keys if k.startswith("benchmark/")]
+    bench = bench + [bench[0]]  # 224 = 7 warps
+    ids = [keys.index(k) for k in bench]
+    T = 300
+    actions = np.stack([golden.arr(k, "walk_actions") for k in bench], axis=1)
+    n = len(bench)
+    puzzle_id = torch.tensor(ids, dtype=torch.int32, device="cuda")
+    xy = engine.new_state(n)
+    engine.reset(xy, puzzle_id)
+    reward = torch.empty((T, n), dtype=torch.float32, device="cuda")
+    term = torch.empty((T, n), dtype=torch.uint8, device="cuda")
+    counters = torch.zeros(4, dtype=torch.int64, device="cuda")
+    engine.rollout(xy, puzzle_id, torch.from_numpy(actions).cuda(), reward=reward, terminated=term,
+                   counters=counters)
+    final = _pack([golden.arr(k, "walk_states").astype(np.int32)[-1:] for k in bench], engine.n_max)
+    assert np.array_equal(xy.cpu().numpy(), final)
+    ach = np.stack([golden.arr(k, "walk_achieved").astype(np.int32) for k in bench], axis=1)
+    isg = np.stack([golden.arr(k, "walk_isgoal") for k in bench], axis=1)
+    dg = ach[1:] - ach[:-1]
+    assert np.array_equal(term.cpu().numpy().astype(bool), isg[1:])
+    assert np.array_equal(reward.cpu().numpy(), _expected_reward(dg, isg[1:]))
+    c = counters.cpu().numpy()
+    moved_steps = sum(
+        int((np.diff(golden.arr(k, "walk_states").astype(np.int32), axis=0) != 0).any(axis=(1, 2)).sum())
+        for k in bench
+    )
+    assert c.tolist() == [T * n, int(isg[1:].sum()), moved_steps, int(np.maximum(dg, 0).sum())]
+    # single-puzzle launches: 32 copies of the same walk
+    for key in ["benchmark/level4/Mind The Gap", "benchmark/level3/Crow Pulling", "benchmark/level2/Pull Dont Push"]:
+        p = keys.index(key)
+        acts = np.repeat(golden.arr(key, "walk_actions")[:, None], 32, axis=1)
+        xy1 = engine.new_state(32)
+        engine.reset(xy1, p)
+        r1 = torch.empty((T, 32), dtype=torch.float32, device="cuda")
+        t1 = torch.empty((T, 32), dtype=torch.uint8, device="cuda")
+        engine.rollout(xy1, p, torch.from_numpy(np.ascontiguousarray(acts)).cuda(), reward=r1, terminated=t1)
+        e = bench.index(key)
+        assert np.array_equal(r1.cpu().numpy(), np.repeat(reward[:, e:e + 1].cpu().numpy(), 32, axis=1)), key
+        assert np.array_equal(t1.cpu().numpy(), np.repeat(term[:, e:e + 1].cpu().numpy(), 32, axis=1)), key
+        assert np.array_equal(xy1.cpu().numpy()[:, :, 0], xy.cpu().numpy()[:, :, e]), key
