@@ -601,7 +601,14 @@ struct BoardLeanSim {
   __device__ __forceinline__ uint32_t do_step(uint32_t a) {
     return board_step(s, (int)a, acts[(kChecked ? (a & 3u) : a) * kBlock]);
   }
-  __device__ __forceinline__ int achieved() const { return board_achieved(s); }
+  // branch-free (goal[k >= g] is all ones and never matches): the goal count differs per thread
+  // in a mixed batch, so the early exit of board_achieved would diverge
+  __device__ __forceinline__ int achieved() const {
+    int count = 0;
+#pragma unroll
+    for (int k = 0; k + 1 < NMAX; ++k) count += (s.b[k + 1] == s.goal[k]) ? 1 : 0;
+    return count;
+  }
   __device__ __forceinline__ int goals() const { return s.g; }
   __device__ __forceinline__ void store(const StepParams& p, int64_t e) {
 #pragma unroll
