@@ -70,7 +70,7 @@ __device__ __forceinline__ void flush_counts(const StepCounts& c, const StepPara
   }
 }
 
-template <class Sim>
+template <bool kEpisodes, class Sim>
 __device__ __forceinline__ void run_lean_sim(Sim& sim, const StepParams& p, const int64_t e,
                                              const float* s_rlut, uint8_t* tiles, StepCounts& c);
 template <class Env>
@@ -90,7 +90,7 @@ __device__ __forceinline__ void run_steps(Env& env, const StepParams& p, int64_t
       if (active) {
         env.load(p.x, p.y, p.stride, e);
         GeneralLeanSim<Env> sim{env};
-        run_lean_sim(sim, p, e, s_rlut, s_tiles[threadIdx.x >> 5][0], c);
+        run_lean_sim<false>(sim, p, e, s_rlut, s_tiles[threadIdx.x >> 5][0], c);
       }
     } else if (active) {
       run_steps_thread<kLean>(env, p, e, c);
@@ -514,10 +514,15 @@ struct BoardSimMixed {
 // rule: do_step<kChecked>(a) -> moved mask, achieved(), goals(), store(), kCheapAchieved.
 // Whole warps only (the launcher sets p.lean_tiles when N % 32 == 0 and actions are 16-byte aligned).
 // ------------------------------------------------------------------------------------------
-template <class Sim>
+template <bool kEpisodes = false, class Sim>
 __device__ __forceinline__ void run_lean_sim(Sim& sim, const StepParams& p, const int64_t e,
                                              const float* s_rlut, uint8_t* tiles, StepCounts& c) {
-  const int g = sim.goals();
+  // kEpisodes (pw_rollout_episodes): step counter, truncation, and a terminated / truncated
+  // environment restarts on a freshly drawn puzzle (gym_env.py:171-186,223 on the device)
+  int g = sim.goals();
+  int steps = kEpisodes ? p.steps[e] : 0;
+  uint8_t* trunc_base = (kEpisodes && p.truncated) ? p.truncated + (e & 1) : nullptr;
+  asm volatile("" : "+l"(trunc_base));
   const int T = p.T;
   const uint32_t half_n = (uint32_t)(p.N >> 1);
   uint8_t* term_base = p.terminated + (e & 1);
@@ -542,6 +547,19 @@ __device__ __forceinline__ void run_lean_sim(Sim& sim, const StepParams& p, cons
     if (kChecked) n_invalid += a > 3u ? 1u : 0u;
     reward_base[(size_t)h_out * 2u] = r;
     asm volatile("st.global.u8 [%0], %1;" ::"l"(term_base + (size_t)h_out * 2u), "r"(tbyte) : "memory");
+    if constexpr (kEpisodes) {
+      ++steps;
+      const bool trunc = p.max_steps > 0 && steps >= p.max_steps;  // gym_env.py:223
+      if (trunc_base)
+        asm volatile("st.global.u8 [%0], %1;" ::"l"(trunc_base + (size_t)h_out * 2u), "r"(trunc ? 1u : 0u)
+                     : "memory");
+      if (term || trunc) {
+        sim.resample(p, e);
+        g = sim.goals();
+        prev = sim.achieved();
+        steps = 0;
+      }
+    }
     h_out += half_n;
   };
   constexpr int kBlockSteps = 32, kGroup = Sim::kGroup;
@@ -587,6 +605,7 @@ __device__ __forceinline__ void run_lean_sim(Sim& sim, const StepParams& p, cons
   c.dgoals += n_gain;
   c.invalid += n_invalid;
   sim.store(p, e);
+  if (kEpisodes) p.steps[e] = steps;
 }
 
 // boards with the edge-mask rule; `acts` = this thread's per-action constants in shared memory,
@@ -622,12 +641,42 @@ struct BoardLeanSim {
   }
 };
 
+// ... with per-thread puzzles that change at episode boundaries (pw_rollout_episodes)
+template <int NMAX, typename Word>
+struct BoardEpisodeSim : BoardLeanSim<NMAX, Word> {
+  BoardAction<Word>* my_acts;  // the same shared-memory slots, writable
+  __device__ __forceinline__ BoardEpisodeSim(Board<NMAX, Word>& board, BoardAction<Word>* a)
+      : BoardLeanSim<NMAX, Word>{board, a}, my_acts(a) {}
+  __device__ __forceinline__ void resample(const StepParams& p, int64_t e) {
+    const uint32_t episode = p.episode[e] + 1u;
+    p.episode[e] = episode;
+    const int pid = draw_puzzle(p.seed, e, episode, p.num_puzzles);
+    p.puzzle_id_mut[e] = pid;
+    const BoardStaticPod* q = p.board_static + pid;
+    Board<NMAX, Word>& s = this->s;
+    s.wall = (Word)__ldg(&q->wall);
+    s.awall = (Word)__ldg(&q->awall);
+    s.edge_up = (Word)__ldg(&q->edge_up);
+    s.edge_down = (Word)__ldg(&q->edge_down);
+    s.P = __ldg(&q->P);
+    s.n = __ldg(&q->n);
+    s.g = __ldg(&q->g);
+#pragma unroll
+    for (int k = 0; k < NMAX; ++k) {
+      s.goal[k] = (Word)__ldg(&q->goal[k]);
+      s.b[k] = (Word)__ldg(&q->init[k]);
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a) my_acts[a * kBlock] = board_action_of(s, (uint32_t)a);
+  }
+};
+
 template <int NMAX, typename Word>
 __device__ __forceinline__ void run_board_lean(Board<NMAX, Word>& s, const StepParams& p, const int64_t e,
                                                const float* s_rlut, uint8_t* tiles,
                                                const BoardAction<Word>* acts, StepCounts& c) {
   BoardLeanSim<NMAX, Word> sim{s, acts};
-  run_lean_sim(sim, p, e, s_rlut, tiles, c);
+  run_lean_sim<false>(sim, p, e, s_rlut, tiles, c);
 }
 
 // the general rule (collision bit tables) on an Env policy; the (large) rule is not unrolled
@@ -656,11 +705,10 @@ __global__ void __launch_bounds__(kBlock, MIN_BLOCKS)
   __shared__ uint32_t s_counters[4];
   // lean launches only (see run_board_lean): per-warp action tiles, per-thread action constants and a
   // shared-memory copy of the reward table
-  __shared__ __align__(16) uint8_t s_tiles[kLean ? kBlock / 32 : 1][2][kLean ? 32 * 32 : 16];
-  __shared__ BoardAction<Word> s_act[kLean ? 4 : 1][kLean ? kBlock : 1];
-  __shared__ float s_rlut[kLean ? 2 * kMaxObjects + 1 : 1];
-  if (kLean)
-    for (int i = threadIdx.x; i < 2 * kMaxObjects + 1; i += blockDim.x) s_rlut[i] = c_reward_lut[i];
+  __shared__ __align__(16) uint8_t s_tiles[kBlock / 32][2][32 * 32];
+  __shared__ BoardAction<Word> s_act[4][kBlock];
+  __shared__ float s_rlut[2 * kMaxObjects + 1];
+  for (int i = threadIdx.x; i < 2 * kMaxObjects + 1; i += blockDim.x) s_rlut[i] = c_reward_lut[i];
   if (threadIdx.x < 4) s_counters[threadIdx.x] = 0;
   __syncthreads();
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -684,6 +732,12 @@ __global__ void __launch_bounds__(kBlock, MIN_BLOCKS)
       } else {
         general_slow_path_global(tbl.base, p, e, c);
       }
+    } else if (!kLean && p.episode_tiles && __all_sync(0xffffffffu, regular)) {
+      // pw_rollout_episodes made of whole warps: the plain-rollout loop with episode handling
+#pragma unroll
+      for (int a = 0; a < 4; ++a) s_act[a][threadIdx.x] = board_action_of(s, (uint32_t)a);
+      BoardEpisodeSim<NMAX, Word> esim(s, &s_act[0][threadIdx.x]);
+      run_lean_sim<true>(esim, p, e, s_rlut, s_tiles[threadIdx.x >> 5][0], c);
     } else if (regular) {
       run_steps_sim<kLean>(sim, p, e, c);
     } else if (!(p.flags & kFlagResample)) {
@@ -975,7 +1029,12 @@ cudaError_t launch_steps(const StepParams& p_in, int n_limit, cudaStream_t strea
   if (p_in.N == 0 || p_in.T == 0) return cudaSuccess;
   StepParams p = p_in;
   // lean launches made of whole warps with 16-byte aligned actions can stage actions with cp.async
-  p.lean_tiles = is_lean(p) && (p.N & 31) == 0 && (reinterpret_cast<uintptr_t>(p.actions) & 15u) == 0;
+  const bool whole_warps = (p.N & 31) == 0 && (reinterpret_cast<uintptr_t>(p.actions) & 15u) == 0;
+  p.lean_tiles = is_lean(p) && whole_warps;
+  // pw_rollout_episodes in the shape an RL loop uses: reward + terminated (+ truncated) per step
+  p.episode_tiles = whole_warps && p.flags == (kFlagAutoreset | kFlagResample) && p.reward && p.terminated &&
+                    !p.dgoals && !p.moved && !p.return_sum && p.steps && p.puzzle_id_mut && p.episode &&
+                    (int64_t)p.T * p.N < ((int64_t)1 << 32);
   const unsigned grid = grid_for(p.N);
   const size_t state_bytes = (size_t)p.n_max * 2 * kBlock * sizeof(int);
   const bool lean = is_lean(p);

@@ -344,7 +344,8 @@ def test_argument_errors(setup):
     # every puzzle fits a uint32 board
     ["trivial", "multiple_goals", "transitive_pushing", "pushing", "trivial_obstacle"],
 ])
-def test_rollout_episodes_resamples_puzzles_like_the_host_model(golden, names):
+@pytest.mark.parametrize("n", [48, 64])  # 64 = whole warps: the plain-rollout loop with episode handling
+def test_rollout_episodes_resamples_puzzles_like_the_host_model(golden, names, n):
     """pw_rollout_episodes: on termination / truncation an environment draws a new puzzle with
     the documented counter-based generator and restarts; the whole trajectory must equal a host
     simulation with the oracle (reward, terminated, truncated per step; final puzzle, episode,
@@ -354,7 +355,7 @@ def test_rollout_episodes_resamples_puzzles_like_the_host_model(golden, names):
     texts = [golden.text("python3/" + n) for n in names]
     engine = Engine(texts)
     oracles = [po.OraclePuzzle(t) for t in texts]
-    n, T, max_steps, seed = 48, 160, 9, 0xC0FFEE1234
+    T, max_steps, seed = 160, 9, 0xC0FFEE1234
     rng = np.random.default_rng(21)
     actions = rng.integers(0, 4, size=(T, n), dtype=np.uint8)
     pid0 = rng.integers(0, len(texts), size=n).astype(np.int32)
