@@ -33,6 +33,7 @@ PUZZLE_KEY = "level1/Road Block"
 N_ENVS = 1 << 18
 T_STEPS = 1024
 ACTION_SEED = 1234
+ROLLOUT_KERNEL = "k_rollout_ring<3, true> (pw_rollout)"
 
 
 def _workload_config(n_gpus: int) -> dict:
@@ -62,13 +63,14 @@ class ClockSampler:
         self.rows = []  # (arrival time, csv line)
         self.proc = None
         self.thread = None
-        self.t_begin = self.t_end = None
+        self.windows = []  # [begin, end] wall-clock intervals of the timed regions
 
     def mark_begin(self):
-        self.t_begin = time.time()
+        self.windows.append([time.time(), None])
 
     def mark_end(self):
-        self.t_end = time.time()
+        if self.windows and self.windows[-1][1] is None:
+            self.windows[-1][1] = time.time()
 
     def start(self):
         try:
@@ -97,8 +99,8 @@ class ClockSampler:
         sm, sm_max, power, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         inside = [r for t, r in self.rows
-                  if self.t_begin is not None and self.t_begin <= t <= (self.t_end or t) + 0.05]
-        window = "timed region"
+                  if any(b <= t <= (e or t) + 0.05 for b, e in self.windows)]
+        window = "timed regions (device-resident + e2e + configs)"
         if len(inside) < 3:  # very short timed region: use everything since the warm-up started
             inside, window = [r for _, r in self.rows], "warm-up + timed region"
         for row in inside:
@@ -222,10 +224,143 @@ def run_reference(args) -> None:
 
 
 # ---------------------------------------------------------------------------- our arm
+def _peak():
+    peaks_path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    try:
+        with open(peaks_path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except (OSError, KeyError, TypeError, ValueError):
+        return 6650.0, "fallback (B200_PROFILING.md)"  # absent or unreadable: the documented fallback
+
+
+def _timed(fn, reps, warmup, dev, distributed):
+    """Mean ms per call of `fn` over `reps` calls (CUDA events on the current stream, barrier +
+    synchronize on both sides, max over ranks)."""
+    import torch
+
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    distributed.barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    distributed.barrier()
+    return distributed.max_over_ranks(a.elapsed_time(b), dev) / reps
+
+
+def run_configs(rank, world, dev, peak, sampler, reps=5):
+    """BASELINE configs 3, 4, 5 (+ the reference's real level-0 set): device-timed sub-records.
+    Under N GPUs every workload is SHARDED (fixed total size, contiguous slice per rank, strong
+    scaling); the rates are whole-job rates (total units / max-over-ranks time)."""
+    import torch
+
+    from pushworld_b200 import data, distributed
+    from pushworld_b200.engine import Engine
+    from pushworld_b200.vector_env import PushWorldVectorEnv, RolloutOutput
+
+    out = {}
+
+    def record(name, workload, kernel, units, ms, fused_bpu, survey_bpu, extra=None):
+        rate = units / (ms * 1e-3)
+        rec = {"workload": workload, "kernel": kernel, "units": units, "kernel_ms": ms,
+               "units_per_s": rate, "n_gpus": world, "sharded": world > 1,
+               "bytes_per_unit": fused_bpu, "achieved_gbs": rate * fused_bpu / 1e9,
+               "frac": rate * fused_bpu / 1e9 / (peak * world)}
+        if survey_bpu is not None:
+            rec["survey_8d"] = {"bytes_per_unit": survey_bpu, "achieved_gbs": rate * survey_bpu / 1e9,
+                                "frac": rate * survey_bpu / 1e9 / (peak * world)}
+        if extra:
+            rec.update(extra)
+        out[name] = rec
+
+    # ---- config 3: all 223 benchmark puzzles, N = 2^18, T = 1024 ---------------------------
+    keys = data.benchmark_keys()
+    texts = [data.puzzle_text(k) for k in keys]
+    n_total, T = 1 << 18, 1024
+    for name, ids in (("cfg3_grouped", None),
+                      ("cfg3_interleaved", torch.arange(n_total, dtype=torch.int64) % len(keys))):
+        env = PushWorldVectorEnv(texts, n_total, puzzle_ids=ids, device=dev, shard=True)
+        n = env.num_envs
+        gen = torch.Generator(device=dev).manual_seed(1235 + rank)
+        actions = torch.randint(0, 4, (T, n), dtype=torch.uint8, device=dev, generator=gen)
+        ro = RolloutOutput(reward=torch.empty((T, n), dtype=torch.float32, device=dev),
+                           terminated=torch.empty((T, n), dtype=torch.uint8, device=dev),
+                           counters=torch.zeros(4, dtype=torch.int64, device=dev))
+
+        def run():
+            env.reset()
+            env.rollout(actions, out=ro)  # incl. the per-rollout counter all-reduce
+
+        sampler.mark_begin()
+        ms = _timed(run, reps, 2, dev, distributed)
+        sampler.mark_end()
+        n_obj = torch.tensor([p.num_objects for p in env.engine.parsed], dtype=torch.float64)[
+            (torch.arange(n_total) % len(keys))].mean().item()
+        record(name,
+               f"cfg3: 2^18 envs over all {len(keys)} benchmark puzzles "
+               f"({'grouped by puzzle' if ids is None else 'env e -> puzzle e mod 223'}), T=1024, "
+               "reward f32 + terminated u8 per step",
+               "k_rollout_occ (general rule: occupancy reject + batched push closure)",
+               n_total * T, ms, 6.0 + 16.0 * n_obj / T, 16.0 * n_obj + 6.0, {"unit": "env-steps"})
+        del env, actions, ro
+    torch.cuda.empty_cache()
+
+    # ---- config 4: successor expansion of a 10M-state frontier ------------------------------
+    eng = Engine([data.puzzle_text("level2/Pull Dont Push")], device=dev)
+    lo, hi = distributed.shard_range(10_000_000, rank, world)
+    n = hi - lo
+    xy = eng.new_state(n)
+    eng.reset(xy, 0)
+    gen = torch.Generator(device=dev).manual_seed(1236 + rank)
+    walk = torch.randint(0, 4, (64, n), dtype=torch.uint8, device=dev, generator=gen)
+    eng.rollout(xy, 0, walk)  # frontier = 64-step seeded random walks
+    del walk
+    xy_out = torch.empty((2, eng.n_max, 4 * n), dtype=torch.int32, device=dev)
+    moved = torch.empty(4 * n, dtype=torch.int32, device=dev)
+    goal = torch.empty(4 * n, dtype=torch.uint8, device=dev)
+    sampler.mark_begin()
+    ms = _timed(lambda: eng.expand(xy, 0, xy_out=xy_out, moved=moved, goal=goal), reps, 2, dev, distributed)
+    sampler.mark_end()
+    record("cfg4_expand", "cfg4: level2/Pull Dont Push, 10M-state frontier -> 40M successors + moved mask + goal flag",
+           "k_expand_uniform<8>", 40_000_000, ms, 10.0 * eng.n_max + 5.0, 10.0 * eng.n_max + 5.0,
+           {"unit": "successors"})
+    del xy_out, moved, goal, xy, eng
+    torch.cuda.empty_cache()
+
+    # ---- config 5: step + RGB observation, 2^16 environments --------------------------------
+    eng = Engine([data.puzzle_text(PUZZLE_KEY)], device=dev)
+    lo, hi = distributed.shard_range(1 << 16, rank, world)
+    n = hi - lo
+    xy = eng.new_state(n)
+    eng.reset(xy, 0)
+    act = torch.randint(0, 4, (n,), dtype=torch.uint8, device=dev)
+    for dtype, size in (("float32", 4), ("uint8", 1)):
+        obs = torch.empty((n, 100, 160, 3), dtype=torch.float32 if size == 4 else torch.uint8, device=dev)
+        step_out = eng.step_render(xy, 0, act, dtype=dtype, out=obs)[1]
+        sampler.mark_begin()
+        ms = _timed(lambda: eng.step_render(xy, 0, act, dtype=dtype, out=obs, step_out=step_out),
+                    reps, 2, dev, distributed)
+        sampler.mark_end()
+        record(f"cfg5_step_render_{'f32' if size == 4 else 'u8'}",
+               f"cfg5: {PUZZLE_KEY}, 2^16 envs, pw_step_render, {dtype} observation (100,160,3)",
+               "k_step + k_render", 1 << 16, ms, 100 * 160 * 3 * size + 54.0, 100 * 160 * 3 * size + 54.0,
+               {"unit": "frames"})
+        del obs
+    del eng, xy
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_ours(args) -> None:
     import torch
 
     from pushworld_b200 import data, distributed
+    from pushworld_b200.engine import record_to_outputs
     from pushworld_b200.vector_env import PushWorldVectorEnv, RolloutOutput
 
     if not torch.cuda.is_available():
@@ -233,6 +368,8 @@ def run_ours(args) -> None:
     rank, local_rank, world = distributed.init_from_env("nccl")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # pinned host buffers (the e2e legs) are allocated after this: local to the GPU's NUMA node
+    numa = distributed.bind_to_gpu_numa_node(local_rank)
 
     env = PushWorldVectorEnv([data.puzzle_text(PUZZLE_KEY)], N_ENVS, puzzle_ids=0, device=dev)
     n_obj = env.engine.n_max
@@ -243,24 +380,44 @@ def run_ours(args) -> None:
         terminated=torch.empty((T_STEPS, N_ENVS), dtype=torch.uint8, device=dev),
         counters=torch.zeros(4, dtype=torch.int64, device=dev),
     )
+    # The path's single collective: ONE all-reduce (sum) of the int64[4] counter vector PER ROLLOUT.
+    # It runs on a side stream and overlaps the next rollout (counter vectors are double buffered).
+    side = torch.cuda.Stream(dev)
+    counters = [torch.zeros(4, dtype=torch.int64, device=dev) for _ in range(2)]
+    reduced = [torch.zeros(4, dtype=torch.int64, device=dev) for _ in range(2)]
+    totals = torch.zeros(4, dtype=torch.int64, device=dev)
+    ev_done = [torch.cuda.Event() for _ in range(2)]
+    ev_free = [torch.cuda.Event() for _ in range(2)]
 
-    def one_step(ev0=None, ev1=None):
+    def one_step(k, ev0=None, ev1=None):
+        b = k & 1
+        cur = torch.cuda.current_stream(dev)
+        cur.wait_event(ev_free[b])  # the all-reduce of rollout k-2 has consumed counters[b]
+        counters[b].zero_()
+        out.counters = counters[b]
         env.reset()
         if ev0 is not None:
             ev0.record()
         env.rollout(actions, out=out)
         if ev1 is not None:
             ev1.record()
+        ev_done[b].record(cur)
+        with torch.cuda.stream(side):
+            side.wait_event(ev_done[b])
+            reduced[b].copy_(counters[b])
+            distributed.allreduce_counters(reduced[b])  # NCCL, int64[4]
+            totals.add_(reduced[b])
+            ev_free[b].record(side)
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    for _ in range(args.warmup):
-        one_step()
+    for k in range(args.warmup):
+        one_step(k)
     torch.cuda.synchronize()
 
     # ---- timed region: device-resident inputs ------------------------------------------
-    out.counters.zero_()
+    totals.zero_()
     kernel_events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
                      for _ in range(args.steps)]
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -269,48 +426,68 @@ def run_ours(args) -> None:
     sampler.mark_begin()
     start.record()
     for k in range(args.steps):
-        one_step(*kernel_events[k])
-    totals = out.counters.clone()
-    distributed.allreduce_counters(totals)  # the path's single collective (NCCL, int64[4])
+        one_step(k, *kernel_events[k])
+    torch.cuda.current_stream(dev).wait_stream(side)  # the last all-reduce is part of the job
     stop.record()
     torch.cuda.synchronize()
     sampler.mark_end()
     distributed.barrier()
-    clocks = sampler.stop() if rank == 0 else None
     elapsed_ms = distributed.max_over_ranks(start.elapsed_time(stop), dev)
     total_env_steps = int(totals[0].item())
     assert total_env_steps == world * args.steps * N_ENVS * T_STEPS, total_env_steps
     value = total_env_steps / (elapsed_ms * 1e-3)
     kernel_ms = statistics.mean(a.elapsed_time(b) for a, b in kernel_events)
+    out.counters = counters[0]
 
     # ---- end to end: pinned host buffers in, pinned host buffers out ---------------------
+    # (1) the headline: actions in (1 B / env-step), packed per-step records out (1 B / env-step)
     h_act = torch.empty((T_STEPS, N_ENVS), dtype=torch.uint8).pin_memory()
     h_act.copy_(actions)
+    h_rec = torch.empty((T_STEPS, N_ENVS), dtype=torch.uint8).pin_memory()
+    e2e_steps = min(args.steps, 40)
+    chunks = (T_STEPS + 63) // 64
+
+    def e2e_leg(step_fn):
+        for _ in range(min(args.warmup, 3)):
+            step_fn()
+        distributed.barrier()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sampler.mark_begin()
+        a.record()
+        for _ in range(e2e_steps):
+            step_fn()
+        b.record()
+        torch.cuda.synchronize()
+        sampler.mark_end()
+        ms = distributed.max_over_ranks(a.elapsed_time(b), dev)
+        return ms, world * e2e_steps * N_ENVS * T_STEPS / (ms * 1e-3)
+
+    def e2e_packed_step():
+        env.reset()
+        env.rollout_host_packed(h_act, h_rec, chunk_steps=64)
+
+    e2e_ms, e2e_value = e2e_leg(e2e_packed_step)
+    # the records must expand to exactly the float32 rewards / flags of the device-resident run
+    r_last, t_last, _, _ = record_to_outputs(h_rec[-1])
+    assert torch.equal(r_last, out.reward[-1].cpu()) and torch.equal(t_last, out.terminated[-1].cpu())
+    r_mid, t_mid, _, _ = record_to_outputs(h_rec[T_STEPS // 2, : 1 << 14])
+    assert torch.equal(r_mid, out.reward[T_STEPS // 2, : 1 << 14].cpu())
+    del h_rec
+
+    # (2) the same with the reference's own output types: float32 reward + uint8 terminated out (5 B)
     h_rew = torch.empty((T_STEPS, N_ENVS), dtype=torch.float32).pin_memory()
     h_term = torch.empty((T_STEPS, N_ENVS), dtype=torch.uint8).pin_memory()
-    e2e_steps = min(args.steps, 40)  # ~25 ms each (PCIe bound)
 
-    def e2e_step():
+    def e2e_f32_step():
         env.reset()
         env.rollout_host(h_act, h_rew, h_term, chunk_steps=64)
 
-    for _ in range(min(args.warmup, 3)):
-        e2e_step()
-    distributed.barrier()
-    torch.cuda.synchronize()
-    t_start, t_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t_start.record()
-    for _ in range(e2e_steps):
-        e2e_step()
-    t_stop.record()
-    torch.cuda.synchronize()
-    e2e_ms = distributed.max_over_ranks(t_start.elapsed_time(t_stop), dev)
-    e2e_value = world * e2e_steps * N_ENVS * T_STEPS / (e2e_ms * 1e-3)
-    # the device-resident run and the host-buffer run must produce the same bytes
+    e2e_f32_ms, e2e_f32_value = e2e_leg(e2e_f32_step)
     assert torch.equal(h_rew[-1], out.reward[-1].cpu()) and torch.equal(h_term[-1], out.terminated[-1].cpu())
-    chunks = (T_STEPS + 63) // 64
+    del h_rew, h_term
 
-    # ---- end to end, summaries only: host actions in, per-environment returns out ------
+    # (3) summaries only: host actions in, per-environment returns out
     h_ret = torch.empty(N_ENVS, dtype=torch.float32).pin_memory()
     h_nterm = torch.empty(N_ENVS, dtype=torch.int32).pin_memory()
 
@@ -318,31 +495,18 @@ def run_ours(args) -> None:
         env.reset()
         env.rollout_host_returns(h_act, h_ret, h_nterm, chunk_steps=64)
 
-    for _ in range(min(args.warmup, 3)):
-        e2e_returns_step()
-    distributed.barrier()
-    torch.cuda.synchronize()
-    r_start, r_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    r_start.record()
-    for _ in range(e2e_steps):
-        e2e_returns_step()
-    r_stop.record()
-    torch.cuda.synchronize()
-    e2e_ret_ms = distributed.max_over_ranks(r_start.elapsed_time(r_stop), dev)
-    e2e_ret_value = world * e2e_steps * N_ENVS * T_STEPS / (e2e_ret_ms * 1e-3)
+    e2e_ret_ms, e2e_ret_value = e2e_leg(e2e_returns_step)
     assert torch.equal(h_nterm.to(torch.int64), out.terminated.sum(dim=0, dtype=torch.int64).cpu())
+    del h_act, env, actions, out
+    torch.cuda.empty_cache()
 
+    peak, peak_src = _peak()
+    configs = run_configs(rank, world, dev, peak, sampler) if not args.no_configs else {}
+    clocks = sampler.stop() if rank == 0 else None
     if rank != 0:
         return
 
     # ---- roofline of the dominant kernel (pw_rollout) -----------------------------------
-    peaks_path = os.path.join(REPO, "MEASURED_PEAKS.json")
-    peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    try:
-        with open(peaks_path) as f:
-            peak, peak_src = float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-    except (OSError, KeyError, TypeError, ValueError):
-        pass  # absent or unreadable: the documented fallback
     units = N_ENVS * T_STEPS
     # bytes a T-fused rollout must move per env-step: action 1 + reward 4 + terminated 1, plus the
     # state read once and written once per launch (16 n / T).  SURVEY 8(d)'s 16n+6 is the T=1 figure.
@@ -351,7 +515,7 @@ def run_ours(args) -> None:
     achieved = units * fused_bpu / (kernel_ms * 1e-3) / 1e9
     roofline = {
         "bound": "hbm",
-        "kernel": "k_rollout_ring<3, true> (pw_rollout)",
+        "kernel": ROLLOUT_KERNEL,
         "achieved": achieved,
         "peak": peak,
         "unit": "GB/s",
@@ -373,7 +537,8 @@ def run_ours(args) -> None:
         with open(traffic_path) as f:
             traffic = json.load(f)
         roofline["traffic"] = traffic.get("dram_bytes_per_launch")
-        # secondary bound: the kernel is bound by the integer ALU pipe, not by HBM
+        roofline["traffic_source"] = traffic.get("source")
+        # secondary bound: what limits the kernel when it is not HBM
         roofline["secondary_bound"] = traffic.get("secondary_bound")
 
     cpu_rate, cpu_threads, cpu_sample = cpu_port_throughput(12.0)
@@ -401,9 +566,21 @@ def run_ours(args) -> None:
             "value": e2e_value,
             "unit": UNIT,
             "h2d_bytes_per_step": T_STEPS * N_ENVS,
-            "d2h_bytes_per_step": T_STEPS * N_ENVS * 5,
+            "d2h_bytes_per_step": T_STEPS * N_ENVS,
             "ms_per_step": e2e_ms / e2e_steps,
-            "api": "PushWorldVectorEnv.rollout_host (pinned host buffers, 3-stream pipeline)",
+            "api": "PushWorldVectorEnv.rollout_host_packed (pinned host buffers, 3-stream pipeline): "
+            "uint8 actions in, one packed record byte per env-step out (delta_goals | truncated | "
+            "terminated; engine.record_to_outputs expands it to the reference's float reward + flags, "
+            "checked bit-exact against the device-resident run)",
+            "numa": numa,
+        },
+        "e2e_f32": {
+            "value": e2e_f32_value,
+            "unit": UNIT,
+            "h2d_bytes_per_step": T_STEPS * N_ENVS,
+            "d2h_bytes_per_step": T_STEPS * N_ENVS * 5,
+            "ms_per_step": e2e_f32_ms / e2e_steps,
+            "api": "PushWorldVectorEnv.rollout_host (float32 reward + uint8 terminated out: the round-1 e2e)",
         },
         "e2e_summaries": {
             "value": e2e_ret_value,
@@ -414,6 +591,7 @@ def run_ours(args) -> None:
             "api": "PushWorldVectorEnv.rollout_host_returns (per-environment return sum + terminated "
             "count come back; per-step arrays stay on the device)",
         },
+        "configs": configs,
         "gpu_launches": 2 * args.steps,
         "gpu_launches_e2e": (1 + chunks) * e2e_steps,
         "clocks": clocks,
@@ -432,6 +610,8 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--no-configs", action="store_true",
+                    help="skip the BASELINE config 3/4/5 sub-records (headline + e2e only)")
     args = ap.parse_args()
     # The contract is ONE JSON line on stdout.  Libraries may write banners to file descriptor 1
     # (NCCL prints its version there when NCCL_DEBUG is set), so fd 1 is pointed at stderr for the

@@ -64,6 +64,13 @@ extern "C" {
 
 /* pw_rollout flags */
 #define PW_FLAG_AUTORESET 1u /* re-initialise an environment after a terminated/truncated step */
+#define PW_FLAG_RESAMPLE 2u  /* pw_rollout_packed: ... on a freshly drawn puzzle (as pw_rollout_episodes) */
+
+/* the packed per-step record of pw_rollout_packed */
+#define PW_RECORD_DGOALS_MASK 0x3fu /* bits 0..5: delta_goals + PW_RECORD_DGOALS_BIAS */
+#define PW_RECORD_DGOALS_BIAS 32
+#define PW_RECORD_TRUNCATED 0x40u
+#define PW_RECORD_TERMINATED 0x80u
 
 typedef struct PwEngine PwEngine;
 
@@ -120,6 +127,8 @@ PW_API int pw_engine_info(const PwEngine* engine, int* num_puzzles, int* n_max, 
 /* Copies the engine's device-side status block to host: status[0] = number of invalid
  * actions seen since the last poll (then cleared).  SYNCHRONISES `stream`. */
 PW_API int pw_engine_poll(PwEngine* engine, uint64_t status[4], void* stream);
+/* Zeroes the status block on `stream` WITHOUT synchronising (drops counts of earlier launches). */
+PW_API int pw_engine_clear_status(PwEngine* engine, void* stream);
 
 /* Thread-local description of the last error on this thread ("" if none). */
 PW_API const char* pw_last_error(void);
@@ -181,6 +190,23 @@ PW_API int pw_rollout_episodes(PwEngine* engine, int64_t n_envs, int32_t n_steps
                         float* reward, int8_t* dgoals, uint8_t* terminated, uint8_t* truncated,
                         int32_t* steps, int32_t max_steps, float* return_sum, uint64_t* counters,
                         uint64_t seed, uint32_t* episode, void* stream);
+
+/* pw_rollout / pw_rollout_episodes writing ONE BYTE per environment step instead of the separate
+ * reward / dgoals / terminated / truncated arrays: everything PushWorldEnv.step returns besides
+ * the observation (gym_env.py:210-226), in the form a host-side consumer gets over PCIe at a fifth
+ * of the bytes.
+ *   record[T][N] uint8: bits 0..5 = delta_goals + 32, bit 6 = truncated, bit 7 = terminated
+ * from which the reference's values follow exactly:
+ *   reward = terminated ? 10.0 : (double)delta_goals - 0.01          (gym_env.py:212-221)
+ * (pushworld_b200.vector_env.record_to_outputs is the host-side expansion).  flags:
+ * PW_FLAG_AUTORESET as in pw_rollout; PW_FLAG_RESAMPLE = the episode handling of
+ * pw_rollout_episodes (needs puzzle_id, steps, episode; `seed` selects the puzzle draws).
+ * steps / return_sum / counters / episode are nullable as in pw_rollout. */
+PW_API int pw_rollout_packed(PwEngine* engine, int64_t n_envs, int32_t n_steps, int32_t* puzzle_id,
+                      int puzzle_uniform, int32_t* x, int32_t* y, int64_t stride,
+                      const uint8_t* actions, uint8_t* record, int32_t* steps, int32_t max_steps,
+                      float* return_sum, uint64_t* counters, uint32_t flags, uint64_t seed,
+                      uint32_t* episode, void* stream);
 
 /* Goal predicates of every environment's CURRENT state.
  * Replaces: PushWorldPuzzle.count_achieved_goals (puzzle.py:396-407) and is_goal_state

@@ -48,6 +48,12 @@ def lib():
             ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
             ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
         ]
+        _LIB.pwo_expand.restype = None
+        _LIB.pwo_expand.argtypes = [
+            ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
+            ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p,
+            ctypes.c_int,
+        ]
     return _LIB
 
 
@@ -96,6 +102,21 @@ class COraclePuzzle:
         ptr = lambda a: None if a is None else a.ctypes.data_as(ctypes.c_void_p)
         return lib().pwo_rollout(self._h, n_envs, actions.shape[0], ptr(x), ptr(y), n_envs,
                                  ptr(actions), ptr(reward), ptr(terminated), threads)
+
+
+    def expand(self, x, y, threads=0):
+        """x, y: int32 [n, N] -> (x_out [n, 4N], y_out [n, 4N], moved uint32 [4N], goal uint8 [4N]);
+        successor a * N + e = action a applied to state e."""
+        n_states = x.shape[1]
+        assert x.flags.c_contiguous and y.flags.c_contiguous and x.shape[0] == self.n
+        x_out = np.empty((self.n, 4 * n_states), np.int32)
+        y_out = np.empty((self.n, 4 * n_states), np.int32)
+        moved = np.empty(4 * n_states, np.uint32)
+        goal = np.empty(4 * n_states, np.uint8)
+        ptr = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+        lib().pwo_expand(self._h, n_states, ptr(x), ptr(y), n_states, ptr(x_out), ptr(y_out),
+                         4 * n_states, ptr(moved), ptr(goal), threads)
+        return x_out, y_out, moved, goal
 
 
 def max_threads():

@@ -241,6 +241,39 @@ int64_t pwo_rollout(const PwoPuzzle *p, int64_t n_envs, int n_steps, int32_t *x,
   return n_envs * (int64_t)n_steps;
 }
 
+/* Successor expansion of n_states states of ONE puzzle (cpp/include/search/best_first_search.h:
+ * 76-92: 4 x getNextState + satisfiesGoal per node).  Successor s = a * n_states + e, SoA like
+ * pw_expand: x_out[j * stride_out + s].  moved: uint32 mask as in cpp/src/pushworld_puzzle.cc:
+ * 439-452; goal: uint8.  moved / goal may be NULL. */
+void pwo_expand(const PwoPuzzle *p, int64_t n_states, const int32_t *x, const int32_t *y,
+                int64_t stride, int32_t *x_out, int32_t *y_out, int64_t stride_out,
+                uint32_t *moved, uint8_t *goal, int threads) {
+  const int n = p->n;
+#ifdef _OPENMP
+  if (threads > 0) omp_set_num_threads(threads);
+#else
+  (void)threads;
+#endif
+#pragma omp parallel for schedule(static)
+  for (int64_t e = 0; e < n_states; ++e) {
+    for (int a = 0; a < 4; ++a) {
+      int xy[2 * PWO_MAX_OBJ];
+      for (int k = 0; k < n; ++k) {
+        xy[2 * k] = x[k * stride + e];
+        xy[2 * k + 1] = y[k * stride + e];
+      }
+      const uint64_t m = pwo_step(p, xy, a);
+      const int64_t s = (int64_t)a * n_states + e;
+      for (int k = 0; k < n; ++k) {
+        x_out[k * stride_out + s] = xy[2 * k];
+        y_out[k * stride_out + s] = xy[2 * k + 1];
+      }
+      if (moved) moved[s] = (uint32_t)m;
+      if (goal) goal[s] = (uint8_t)(pwo_achieved(p, xy) == p->g);
+    }
+  }
+}
+
 int pwo_max_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

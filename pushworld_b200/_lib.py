@@ -16,6 +16,7 @@ PW_OK = 0
 PW_E_INVALID, PW_E_CUDA, PW_E_FORMAT, PW_E_LIMIT, PW_E_NOMEM = -1, -2, -3, -4, -5
 PW_DTYPE_U8, PW_DTYPE_F32 = 0, 1
 PW_FLAG_AUTORESET = 1
+PW_FLAG_RESAMPLE = 2
 ABI_VERSION = 1
 
 # every symbol include/pushworld_b200.h declares, with its argument types
@@ -33,6 +34,7 @@ SIGNATURES = {
         [c_void_p, POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_int)],
     ),
     "pw_engine_poll": (c_int, [c_void_p, POINTER(c_uint64), c_void_p]),
+    "pw_engine_clear_status": (c_int, [c_void_p, c_void_p]),
     "pw_reset": (
         c_int,
         [c_void_p, c_int64, c_void_p, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p],
@@ -53,6 +55,11 @@ SIGNATURES = {
         [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
          c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_uint64, c_void_p,
          c_void_p],
+    ),
+    "pw_rollout_packed": (
+        c_int,
+        [c_void_p, c_int64, c_int32, c_void_p, c_int, c_void_p, c_void_p, c_int64, c_void_p,
+         c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_uint32, c_uint64, c_void_p, c_void_p],
     ),
     "pw_goals": (
         c_int,

@@ -21,9 +21,11 @@ NVCC_FLAGS = [
     "arch=compute_100a,code=sm_100a",
     "-Xcompiler",
     "-fPIC,-fvisibility=hidden",
-    "-shared",
 ]
-SOURCES = ["pw_unity.cu", "pw_compile.cpp"]
+# one object per translation unit, compiled in parallel and linked into one shared library; no
+# relocatable device code: every kernel file is self-contained (device tables that several files
+# need are uploaded once per file)
+SOURCES = ["pw_kernels.cu", "pw_occ.cu", "pw_render.cu", "pw_abi.cu", "pw_compile.cpp"]
 
 
 def _nvcc() -> str:
@@ -77,15 +79,38 @@ def build(force: bool = False, verbose: bool = False) -> str:
             if not force and not _stale():  # another process built it while this one waited
                 return LIB_PATH
             tmp = f"{LIB_PATH}.tmp.{os.getpid()}"
-            cmd = [_nvcc(), *NVCC_FLAGS]
-            if verbose:
-                cmd += ["-Xptxas", "-v"]
-            cmd += [os.path.join(CSRC, s) for s in SOURCES] + ["-o", tmp]
-            proc = subprocess.run(cmd, capture_output=True, text=True)
-            if proc.returncode != 0:
-                if os.path.exists(tmp):
+            obj_dir = os.path.join(LIB_DIR, f"obj.{os.getpid()}")
+            os.makedirs(obj_dir, exist_ok=True)
+
+            def compile_one(src):
+                obj = os.path.join(obj_dir, os.path.splitext(src)[0] + ".o")
+                cmd = [_nvcc(), *NVCC_FLAGS]
+                if verbose:
+                    cmd += ["-Xptxas", "-v"]
+                cmd += ["-c", os.path.join(CSRC, src), "-o", obj]
+                proc = subprocess.run(cmd, capture_output=True, text=True)
+                return obj, cmd, proc
+
+            try:
+                from concurrent.futures import ThreadPoolExecutor
+
+                with ThreadPoolExecutor(max_workers=len(SOURCES)) as pool:
+                    results = list(pool.map(compile_one, SOURCES))
+                log = ""
+                for obj, cmd, proc in results:
+                    if proc.returncode != 0:
+                        raise RuntimeError(f"nvcc failed:\n{' '.join(cmd)}\n{proc.stdout}\n{proc.stderr}")
+                    log += proc.stderr
+                cmd = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a",
+                       *[obj for obj, _, _ in results], "-o", tmp]
+                proc = subprocess.run(cmd, capture_output=True, text=True)
+                if proc.returncode != 0:
+                    raise RuntimeError(f"link failed:\n{' '.join(cmd)}\n{proc.stdout}\n{proc.stderr}")
+                proc.stderr = log + proc.stderr
+            finally:
+                shutil.rmtree(obj_dir, ignore_errors=True)
+                if os.path.exists(tmp) and os.path.getsize(tmp) == 0:
                     os.remove(tmp)
-                raise RuntimeError(f"nvcc failed:\n{' '.join(cmd)}\n{proc.stdout}\n{proc.stderr}")
             os.replace(tmp, LIB_PATH)
             with open(STAMP_PATH + f".tmp.{os.getpid()}", "w") as f:
                 f.write(_sources_digest() + "\n")

@@ -196,7 +196,7 @@ int pw_engine_create(const void* blob, size_t blob_bytes, const uint32_t* offset
     info.blob_u64 = (int)h[7];
     const size_t n_desc = (size_t)info.n + (size_t)info.g;
     bool ok = h[0] == PW_TABLE_MAGIC && info.n >= 1 && info.n <= PW_MAX_OBJECTS &&
-              info.g < info.n + 1 && info.width >= 3 && info.width <= PW_MAX_WIDTH &&
+              info.g < info.n &&  /* goal objects are movables 1..g: g <= n - 1 */ info.width >= 3 && info.width <= PW_MAX_WIDTH &&
               info.height >= 3 && info.height <= PW_MAX_HEIGHT &&
               off + (size_t)info.size_u64 <= total_u64 && h[6] == PW_TABLE_HEADER_WORDS / 2 &&
               (size_t)h[6] + n_desc * 2 <= (size_t)info.size_u64 &&
@@ -290,9 +290,11 @@ int pw_engine_create(const void* blob, size_t blob_bytes, const uint32_t* offset
     err = upload_palette(&pal[0][0], &palf[0][0], 13);
   }
   if (err == cudaSuccess) {
-    const size_t need = (size_t)e->max_packed_u64 * 8 + (size_t)e->n_max * 2 * 128 * sizeof(int) + 64;
-    err = configure_kernels(need > 48 * 1024 ? need : 48 * 1024);
+    // the opt-in is per process and device, not per engine: always ask for the staging limit, so a
+    // later, smaller engine never lowers what an earlier one needs
+    err = configure_kernels((size_t)1 << 30);
   }
+  if (err == cudaSuccess) err = configure_occ_kernels();
   if (err == cudaSuccess) err = configure_render_kernels();
   if (err != cudaSuccess) {
     const int rc = cuda_error(err, "pw_engine_create");
@@ -336,6 +338,15 @@ int pw_engine_poll(PwEngine* e, uint64_t status[4], void* stream) {
   if (err != cudaSuccess) return cuda_error(err, "pw_engine_poll");
   for (int i = 0; i < 4; ++i) status[i] = host[i];
   return PW_OK;
+}
+
+int pw_engine_clear_status(PwEngine* e, void* stream) {
+  clear_error();
+  if (e == nullptr) return set_error(PW_E_INVALID, "engine is NULL");
+  DeviceGuard guard(e->device);
+  const cudaError_t err = cudaMemsetAsync(e->d_status, 0, sizeof(unsigned long long) * 4,
+                                          static_cast<cudaStream_t>(stream));
+  return err == cudaSuccess ? PW_OK : cuda_error(err, "pw_engine_clear_status");
 }
 
 int pw_reset(PwEngine* e, int64_t n_envs, const int32_t* puzzle_id, int puzzle_uniform, int32_t* x,
@@ -454,6 +465,59 @@ int pw_rollout_episodes(PwEngine* e, int64_t n_envs, int32_t n_steps, int32_t* p
   p.num_puzzles = (int32_t)e->puzzles.size();
   const cudaError_t err = launch_steps(p, e->n_max, static_cast<cudaStream_t>(stream));
   return err == cudaSuccess ? PW_OK : cuda_error(err, "pw_rollout_episodes");
+}
+
+int pw_rollout_packed(PwEngine* e, int64_t n_envs, int32_t n_steps, int32_t* puzzle_id,
+                      int puzzle_uniform, int32_t* x, int32_t* y, int64_t stride, const uint8_t* actions,
+                      uint8_t* record, int32_t* steps, int32_t max_steps, float* return_sum,
+                      uint64_t* counters, uint32_t flags, uint64_t seed, uint32_t* episode, void* stream) {
+  clear_error();
+  const int rc = check_common(e, n_envs, puzzle_id, puzzle_uniform, stride, n_envs);
+  if (rc != PW_OK) return rc;
+  PW_RETURN_IF_EMPTY(n_envs);
+  if (n_steps < 0) return set_error(PW_E_INVALID, "negative step count");
+  if (x == nullptr || y == nullptr || actions == nullptr || record == nullptr)
+    return set_error(PW_E_INVALID, "x / y / actions / record is NULL");
+  if (flags & ~(PW_FLAG_AUTORESET | PW_FLAG_RESAMPLE)) return set_error(PW_E_INVALID, "unknown flag");
+  const bool resample = (flags & PW_FLAG_RESAMPLE) != 0;
+  if (resample && (puzzle_id == nullptr || steps == nullptr || episode == nullptr))
+    return set_error(PW_E_INVALID, "PW_FLAG_RESAMPLE needs puzzle_id, steps and episode");
+  DeviceGuard guard(e->device);
+  StepParams p{};
+  p.blob = e->d_blob;
+  p.puzzle_off = e->d_off;
+  p.N = n_envs;
+  p.T = n_steps;
+  p.puzzle_id = puzzle_id;
+  p.puzzle_uniform = puzzle_id ? 0 : puzzle_uniform;
+  p.uniform_u64 = puzzle_id ? 0 : e->puzzles[(size_t)puzzle_uniform].size_u64;
+  p.n_max = e->n_max;
+  p.board_bits = puzzle_id ? e->board_bits_all : e->board_bits[(size_t)puzzle_uniform];
+  if (!puzzle_id) {
+    const PuzzleInfo& info = e->puzzles[(size_t)puzzle_uniform];
+    if (p.board_bits <= 32 && ring_fits(p.board_bits, info.width - 1)) p.ring_goals = info.g;
+  }
+  p.board_static = puzzle_id ? e->d_board_static : e->d_board_static + puzzle_uniform;
+  p.x = x;
+  p.y = y;
+  p.stride = stride;
+  p.actions = actions;
+  p.record = record;
+  p.steps = steps;
+  p.max_steps = max_steps;
+  p.return_sum = return_sum;
+  p.counters = reinterpret_cast<unsigned long long*>(counters);
+  p.status = e->d_status;
+  p.flags = resample ? (kFlagAutoreset | kFlagResample) : (flags & PW_FLAG_AUTORESET ? kFlagAutoreset : 0u);
+  if (resample) {
+    p.puzzle_id_mut = puzzle_id;
+    p.episode = episode;
+    p.seed = seed;
+    p.num_puzzles = (int32_t)e->puzzles.size();
+  }
+  const cudaError_t err = launch_steps(p, resample ? e->n_max : n_limit_of(e, puzzle_id, puzzle_uniform),
+                                       static_cast<cudaStream_t>(stream));
+  return err == cudaSuccess ? PW_OK : cuda_error(err, "pw_rollout_packed");
 }
 
 int pw_step(PwEngine* e, int64_t n_envs, const int32_t* puzzle_id, int puzzle_uniform, int32_t* x,

@@ -216,6 +216,10 @@ int compile_puzzle(const char* text, size_t len, std::vector<uint8_t>* out) {
     }
     const uint32_t off = push_rows(rows_of(s.rel, s.h));
     if (off > 0xffffu) return set_error(PW_E_LIMIT, "puzzle geometry exceeds the 16-bit row offset");
+    // the descriptor (and the pair windows of pw_fast.cuh) hold bounding boxes in 8 bits
+    if (s.h > 255 || s.w > PW_MAX_WIDTH)
+      return set_error(PW_E_LIMIT, "an object's bounding box exceeds " + std::to_string(PW_MAX_WIDTH) +
+                                       " columns x 255 rows");
     desc.push_back(off | ((uint32_t)s.w << 16) | ((uint32_t)s.h << 24));
     desc.push_back(((uint32_t)s.origin.first & 0xffffu) | (((uint32_t)s.origin.second & 0xffffu) << 16));
     desc.push_back(goal_word);

@@ -30,6 +30,7 @@ struct StepParams {
   int32_t board_bits;   // bits puzzle_uniform needs in board form if it is regular, else 1 << 30
   int32_t ring_goals;   // > 0: puzzle_uniform fits ring boards (pw_board.cuh), value = its goal count
   int32_t lean_tiles;   // set by launch_steps: lean shape, N % 32 == 0, 16-byte aligned actions
+  int32_t occ_batch;    // set by launch_rollout_occ: parked lanes that trigger a closure pass
   int32_t episode_tiles;  // set by launch_steps: pw_rollout_episodes with reward + terminated (+ truncated), whole warps
   const BoardStaticPod* board_static;  // device; entry of puzzle_uniform (valid if board_bits <= 64)
   int32_t* x;
@@ -40,6 +41,7 @@ struct StepParams {
   int8_t* dgoals;
   uint8_t* terminated;
   uint8_t* truncated;
+  uint8_t* record;  // [T][N] or nullptr: packed per-step record (pw_rollout_packed), see record_byte()
   uint32_t* moved;
   int32_t* steps;  // [N] in/out or nullptr
   int32_t max_steps;
@@ -150,6 +152,10 @@ cudaError_t configure_kernels(size_t max_dynamic_smem);
 cudaError_t configure_render_kernels();
 // n_limit: max objects over the puzzles this launch can touch (selects the register policy)
 cudaError_t launch_steps(const StepParams& p, int n_limit, cudaStream_t stream);
+// pw_occ.cu: plain / packed rollouts of the general rule (occupancy reject + batched closure)
+bool occ_rollout_eligible(const StepParams& p);
+cudaError_t launch_rollout_occ(const StepParams& p, cudaStream_t stream);
+cudaError_t configure_occ_kernels();
 cudaError_t launch_expand(const ExpandParams& p, int n_limit, cudaStream_t stream);
 cudaError_t launch_reset(const ResetParams& p, cudaStream_t stream);
 cudaError_t launch_goals(const GoalParams& p, cudaStream_t stream);

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cstdlib>
 #include <type_traits>
 
 #include "pw_board.cuh"
@@ -31,48 +32,16 @@ __device__ __forceinline__ void stage_table(uint64_t* dst, const uint64_t* src, 
   __syncthreads();
 }
 
-__device__ __forceinline__ uint32_t warp_sum(uint32_t v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-
-// ------------------------------------------------------------------------------------------
-// T fused steps of one environment per thread (pw_steps.cuh) + block-level counter flush.
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void flush_counts(const StepCounts& c, const StepParams& p,
-                                             uint32_t* s_counters) {
-  // Launches without a counter vector (pw_step, pw_step_render) only report invalid actions, which
-  // are rare: one block-wide vote decides whether anything has to be reduced at all.
-  if (!p.counters && !__syncthreads_or(c.invalid != 0u)) return;
-  if (p.counters || p.status) {
-    const uint32_t c_term = warp_sum(c.terminated), c_moved = warp_sum(c.moved);
-    const uint32_t c_dg = warp_sum(c.dgoals), c_invalid = warp_sum(c.invalid);
-    if ((threadIdx.x & 31) == 0) {
-      if (c_term) atomicAdd(&s_counters[0], c_term);
-      if (c_moved) atomicAdd(&s_counters[1], c_moved);
-      if (c_dg) atomicAdd(&s_counters[2], c_dg);
-      if (c_invalid) atomicAdd(&s_counters[3], c_invalid);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      if (p.counters) {
-        const int64_t first = (int64_t)blockIdx.x * blockDim.x;
-        const int64_t rest = p.N - first;
-        const int64_t live = rest < (int64_t)blockDim.x ? rest : (int64_t)blockDim.x;
-        atomicAdd(&p.counters[0], (unsigned long long)(live > 0 ? live : 0) * (unsigned long long)p.T);
-        if (s_counters[0]) atomicAdd(&p.counters[1], (unsigned long long)s_counters[0]);
-        if (s_counters[1]) atomicAdd(&p.counters[2], (unsigned long long)s_counters[1]);
-        if (s_counters[2]) atomicAdd(&p.counters[3], (unsigned long long)s_counters[2]);
-      }
-      if (p.status && s_counters[3]) atomicAdd(&p.status[0], (unsigned long long)s_counters[3]);
-    }
-  }
-}
-
-template <bool kEpisodes, class Sim>
+template <bool kEpisodes, bool kPacked, class Sim>
 __device__ __forceinline__ void run_lean_sim(Sim& sim, const StepParams& p, const int64_t e,
                                              const float* s_rlut, uint8_t* tiles, StepCounts& c);
+// dispatch on the output shape: reward + terminated, or one packed record byte per step
+template <bool kEpisodes, class Sim>
+__device__ __forceinline__ void run_lean_sim_any(Sim& sim, const StepParams& p, const int64_t e,
+                                                 const float* s_rlut, uint8_t* tiles, StepCounts& c) {
+  if (p.record) run_lean_sim<kEpisodes, true>(sim, p, e, s_rlut, tiles, c);
+  else run_lean_sim<kEpisodes, false>(sim, p, e, s_rlut, tiles, c);
+}
 template <class Env>
 struct GeneralLeanSim;
 
@@ -90,7 +59,7 @@ __device__ __forceinline__ void run_steps(Env& env, const StepParams& p, int64_t
       if (active) {
         env.load(p.x, p.y, p.stride, e);
         GeneralLeanSim<Env> sim{env};
-        run_lean_sim<false>(sim, p, e, s_rlut, s_tiles[threadIdx.x >> 5][0], c);
+        run_lean_sim_any<false>(sim, p, e, s_rlut, s_tiles[threadIdx.x >> 5][0], c);
       }
     } else if (active) {
       run_steps_thread<kLean>(env, p, e, c);
@@ -281,7 +250,7 @@ __global__ void __launch_bounds__(kBlock, MIN_BLOCKS)
 // terminated flag of the one-goal case (kG1) and everything derived from it are multiply-adds,
 // and actions come out of shared-memory tiles filled by cp.async a block of steps ahead.
 // ------------------------------------------------------------------------------------------
-template <int NMAX, bool kG1>
+template <int NMAX, bool kG1, bool kPacked>
 __device__ __forceinline__ void run_ring_lean(const Board<NMAX, uint32_t>& s, const StepParams& p,
                                               const int64_t e, const float* s_r4, uint8_t* tiles,
                                               StepCounts& c) {
@@ -301,7 +270,8 @@ __device__ __forceinline__ void run_ring_lean(const Board<NMAX, uint32_t>& s, co
   // every address is one IMAD.WIDE (h times 2 or 8 bytes, plus a per-thread base) on the FMA pipe.
   // (A multiplier of 1 would be strength-reduced to an add-with-carry pair on the ALU pipe.)
   const uint32_t half_n = (uint32_t)(p.N >> 1);
-  uint8_t* term_base = p.terminated + (e & 1);
+  // kPacked (pw_rollout_packed): ONE record byte per step instead of reward + terminated
+  uint8_t* term_base = (kPacked ? p.record : p.terminated) + (e & 1);
   float* const reward_base = p.reward + (e & 1);
   // keep the byte base an opaque per-thread register pair: otherwise the compiler splits it back
   // into (uniform pointer) + (offset) and adds the pointer with a carry pair per access
@@ -318,37 +288,45 @@ __device__ __forceinline__ void run_ring_lean(const Board<NMAX, uint32_t>& s, co
   // kG1: on4 = 4 * (the goal object sat on its goal after the previous step); the reward is
   // s_r4[2 * terminated + previously_on_goal], read with the byte offset 8 * terminated + on4.
   // Everything derived from `terminated` below is a multiply-add, i.e. off the ALU pipe.
-  uint32_t on4 = (kG1 && b[1] == goal0) ? 4u : 0u;
+  // (packed records: the unit is 1 instead of 4, record = 32 + delta_goals + 128 * terminated)
+  constexpr uint32_t kOn = kPacked ? 1u : 4u;
+  uint32_t on4 = (kG1 && b[1] == goal0) ? kOn : 0u;
   uint32_t n_term = 0, n_both4 = 0, n_moved = 0, n_gain = 0, n_invalid = 0;
   auto one_step = [&](const uint32_t a, auto checked) {
     constexpr bool kChecked = decltype(checked)::value;
     const bool valid = kChecked ? a <= 3u : true;
     n_moved += ring_step<NMAX, false>(b, wall, awall, ring_amount_of(amounts, a), valid);
-    uint32_t tbyte;
-    float r;
+    uint32_t tbyte, code = 0;
+    float r = 0.f;
     if (kG1) {
       // puzzle.py:409-411 with one goal object, as a multiply-add: d = board XOR goal < 2^30 (ring
       // boards have at most 30 bits), so the high word of d * -3 is -1 for d != 0 and 0 for d == 0.
       // (A compare would make the flag a predicate and everything derived from it below a select
       // on the ALU pipe; a multiplier of -1 would be strength-reduced to ALU instructions.)
       asm("mad.hi.s32 %0, %1, -3, 1;" : "=r"(tbyte) : "r"(b[1] ^ goal0));
-      r = *reinterpret_cast<const float*>(reinterpret_cast<const char*>(s_r4) + (tbyte * 8u + on4));
+      if (kPacked) {
+        code = tbyte * 129u + ((uint32_t)kMaxObjects - on4);  // delta_goals = on now - on before
+      } else {
+        r = *reinterpret_cast<const float*>(reinterpret_cast<const char*>(s_r4) + (tbyte * 8u + on4));
+      }
       n_both4 += tbyte * on4;
-      on4 = tbyte * 4u;
+      on4 = tbyte * kOn;
     } else {
       const int ach = achieved();
       const bool term = ach == g;
       const int dg = ach - prev;
       prev = ach;
       // gym_env.py:212-221; the float64 value (dg - 0.01) was rounded to float32 once, on the host
-      r = term ? 10.0f : c_reward_lut[dg + kMaxObjects];
+      if (kPacked) code = record_byte(dg, term, false);
+      else r = term ? 10.0f : c_reward_lut[dg + kMaxObjects];
       n_gain += (uint32_t)max(dg, 0);
       tbyte = term ? 1u : 0u;
     }
     n_term += tbyte;
     if (kChecked) n_invalid += valid ? 0u : 1u;
-    reward_base[(size_t)h_out * 2u] = r;
-    asm volatile("st.global.u8 [%0], %1;" ::"l"(term_base + (size_t)h_out * 2u), "r"(tbyte) : "memory");
+    if (!kPacked) reward_base[(size_t)h_out * 2u] = r;
+    asm volatile("st.global.u8 [%0], %1;" ::"l"(term_base + (size_t)h_out * 2u), "r"(kPacked ? code : tbyte)
+                 : "memory");
     h_out += half_n;
   };
   // Actions do not depend on the state, so they are staged a whole block of 32 steps ahead:
@@ -398,7 +376,7 @@ __device__ __forceinline__ void run_ring_lean(const Board<NMAX, uint32_t>& s, co
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   c.terminated += n_term;
   c.moved += n_moved;
-  c.dgoals += kG1 ? n_term - (n_both4 >> 2) : n_gain;  // gained = on the goal now and not before
+  c.dgoals += kG1 ? n_term - n_both4 / kOn : n_gain;  // gained = on the goal now and not before
   c.invalid += n_invalid;
   // positions back from the boards
 #pragma unroll
@@ -451,7 +429,8 @@ __global__ void __launch_bounds__(kBlock, MIN_BLOCKS)
     // The action tiles are filled by whole warps (the launcher guarantees N % 32 == 0, so a warp
     // is full or empty): a warp with any irregular state takes the general rule for all its lanes.
     if (__all_sync(0xffffffffu, regular)) {
-      run_ring_lean<NMAX, kG1>(s, p, e, s_r4, s_tiles[threadIdx.x >> 5][0], c);
+      if (p.record) run_ring_lean<NMAX, kG1, true>(s, p, e, s_r4, s_tiles[threadIdx.x >> 5][0], c);
+      else run_ring_lean<NMAX, kG1, false>(s, p, e, s_r4, s_tiles[threadIdx.x >> 5][0], c);
     } else {
       general_slow_path(smem, p, e, c);
     }
@@ -514,18 +493,19 @@ struct BoardSimMixed {
 // rule: do_step<kChecked>(a) -> moved mask, achieved(), goals(), store(), kCheapAchieved.
 // Whole warps only (the launcher sets p.lean_tiles when N % 32 == 0 and actions are 16-byte aligned).
 // ------------------------------------------------------------------------------------------
-template <bool kEpisodes = false, class Sim>
+template <bool kEpisodes, bool kPacked, class Sim>
 __device__ __forceinline__ void run_lean_sim(Sim& sim, const StepParams& p, const int64_t e,
                                              const float* s_rlut, uint8_t* tiles, StepCounts& c) {
   // kEpisodes (pw_rollout_episodes): step counter, truncation, and a terminated / truncated
   // environment restarts on a freshly drawn puzzle (gym_env.py:171-186,223 on the device)
   int g = sim.goals();
   int steps = kEpisodes ? p.steps[e] : 0;
-  uint8_t* trunc_base = (kEpisodes && p.truncated) ? p.truncated + (e & 1) : nullptr;
+  // kPacked (pw_rollout_packed): one record byte per step carries delta_goals, terminated, truncated
+  uint8_t* trunc_base = (kEpisodes && !kPacked && p.truncated) ? p.truncated + (e & 1) : nullptr;
   asm volatile("" : "+l"(trunc_base));
   const int T = p.T;
   const uint32_t half_n = (uint32_t)(p.N >> 1);
-  uint8_t* term_base = p.terminated + (e & 1);
+  uint8_t* term_base = (kPacked ? p.record : p.terminated) + (e & 1);
   float* const reward_base = p.reward + (e & 1);
   asm volatile("" : "+l"(term_base));  // see run_ring_lean
   uint32_t h_out = (uint32_t)(e >> 1);
@@ -539,17 +519,25 @@ __device__ __forceinline__ void run_lean_sim(Sim& sim, const StepParams& p, cons
     const int dg = ach - prev;
     prev = ach;
     // gym_env.py:212-221; the float64 value (dg - 0.01) was rounded to float32 once, on the host
-    const float r = term ? 10.0f : s_rlut[dg + kMaxObjects];
     const uint32_t tbyte = term ? 1u : 0u;
     n_term += tbyte;
     n_moved += moved ? 1u : 0u;
     n_gain += (uint32_t)max(dg, 0);
     if (kChecked) n_invalid += a > 3u ? 1u : 0u;
-    reward_base[(size_t)h_out * 2u] = r;
-    asm volatile("st.global.u8 [%0], %1;" ::"l"(term_base + (size_t)h_out * 2u), "r"(tbyte) : "memory");
+    bool trunc = false;
     if constexpr (kEpisodes) {
       ++steps;
-      const bool trunc = p.max_steps > 0 && steps >= p.max_steps;  // gym_env.py:223
+      trunc = p.max_steps > 0 && steps >= p.max_steps;  // gym_env.py:223
+    }
+    if (kPacked) {
+      asm volatile("st.global.u8 [%0], %1;" ::"l"(term_base + (size_t)h_out * 2u),
+                   "r"(record_byte(dg, term, trunc))
+                   : "memory");
+    } else {
+      reward_base[(size_t)h_out * 2u] = term ? 10.0f : s_rlut[dg + kMaxObjects];
+      asm volatile("st.global.u8 [%0], %1;" ::"l"(term_base + (size_t)h_out * 2u), "r"(tbyte) : "memory");
+    }
+    if constexpr (kEpisodes) {
       if (trunc_base)
         asm volatile("st.global.u8 [%0], %1;" ::"l"(trunc_base + (size_t)h_out * 2u), "r"(trunc ? 1u : 0u)
                      : "memory");
@@ -676,7 +664,7 @@ __device__ __forceinline__ void run_board_lean(Board<NMAX, Word>& s, const StepP
                                                const float* s_rlut, uint8_t* tiles,
                                                const BoardAction<Word>* acts, StepCounts& c) {
   BoardLeanSim<NMAX, Word> sim{s, acts};
-  run_lean_sim<false>(sim, p, e, s_rlut, tiles, c);
+  run_lean_sim_any<false>(sim, p, e, s_rlut, tiles, c);
 }
 
 // the general rule (collision bit tables) on an Env policy; the (large) rule is not unrolled
@@ -737,7 +725,7 @@ __global__ void __launch_bounds__(kBlock, MIN_BLOCKS)
 #pragma unroll
       for (int a = 0; a < 4; ++a) s_act[a][threadIdx.x] = board_action_of(s, (uint32_t)a);
       BoardEpisodeSim<NMAX, Word> esim(s, &s_act[0][threadIdx.x]);
-      run_lean_sim<true>(esim, p, e, s_rlut, s_tiles[threadIdx.x >> 5][0], c);
+      run_lean_sim_any<true>(esim, p, e, s_rlut, s_tiles[threadIdx.x >> 5][0], c);
     } else if (regular) {
       run_steps_sim<kLean>(sim, p, e, c);
     } else if (!(p.flags & kFlagResample)) {
@@ -1032,7 +1020,9 @@ cudaError_t launch_steps(const StepParams& p_in, int n_limit, cudaStream_t strea
   const bool whole_warps = (p.N & 31) == 0 && (reinterpret_cast<uintptr_t>(p.actions) & 15u) == 0;
   p.lean_tiles = is_lean(p) && whole_warps;
   // pw_rollout_episodes in the shape an RL loop uses: reward + terminated (+ truncated) per step
-  p.episode_tiles = whole_warps && p.flags == (kFlagAutoreset | kFlagResample) && p.reward && p.terminated &&
+  const bool plain_out = p.reward && p.terminated && !p.record;
+  const bool packed_out = p.record && !p.reward && !p.terminated && !p.truncated;
+  p.episode_tiles = whole_warps && p.flags == (kFlagAutoreset | kFlagResample) && (plain_out || packed_out) &&
                     !p.dgoals && !p.moved && !p.return_sum && p.steps && p.puzzle_id_mut && p.episode &&
                     (int64_t)p.T * p.N < ((int64_t)1 << 32);
   const unsigned grid = grid_for(p.N);
@@ -1061,6 +1051,14 @@ cudaError_t launch_steps(const StepParams& p_in, int n_limit, cudaStream_t strea
   if (p.flags & kFlagResample) {  // puzzles change mid-rollout: dynamic-n policy, global tables
     k_steps_mixed<0, false><<<grid, kBlock, state_bytes, stream>>>(p);
     return cudaGetLastError();
+  }
+  // general rule, plain / packed rollouts made of whole warps: occupancy reject + batched closure
+  // (pw_occ.cu); PW_NO_OCC=1 keeps the scan-every-step kernels below (A/B measurements)
+  {
+    const bool no_occ = getenv("PW_NO_OCC") != nullptr;
+    const bool board_uniform = p.puzzle_id == nullptr && p.board_bits <= 64 && n_limit <= 8 &&
+                               (size_t)p.uniform_u64 * 8 <= kStageLimit;
+    if (!no_occ && !board_uniform && occ_rollout_eligible(p)) return launch_rollout_occ(p, stream);
   }
 #define PW_GO(kernel, smem_bytes)                                         \
   do {                                                                    \

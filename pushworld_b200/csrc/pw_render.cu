@@ -17,7 +17,6 @@
 #include "pw_env.cuh"
 #include "pw_internal.h"
 #include "pw_render_core.cuh"
-#include "pw_steps.cuh"
 
 namespace pw {
 

@@ -11,13 +11,59 @@
 
 namespace pw {
 
-// (float)((double)dg - 0.01) for dg in [-32, 32]; the library is built as ONE translation unit
-// (pw_unity.cu), so this definition is unique.
-__constant__ float c_reward_lut[2 * kMaxObjects + 1];
+// (float)((double)dg - 0.01) for dg in [-32, 32]; one copy per translation unit that includes this
+// header (uploaded by that file's upload function; pw_occ.cu computes the values on the device)
+static __constant__ float c_reward_lut[2 * kMaxObjects + 1];
+
+// The packed per-step record of pw_rollout_packed (include/pushworld_b200.h): everything
+// PushWorldEnv.step returns besides the observation (gym_env.py:210-226) in one byte --
+// bits 0..5 = delta_goals + 32, bit 6 = truncated, bit 7 = terminated.
+__device__ __forceinline__ uint32_t record_byte(int dg, bool term, bool trunc) {
+  return (uint32_t)(dg + kMaxObjects) | (trunc ? 0x40u : 0u) | (term ? 0x80u : 0u);
+}
 
 struct StepCounts {
   uint32_t terminated = 0, moved = 0, dgoals = 0, invalid = 0;
 };
+
+__device__ __forceinline__ uint32_t warp_sum(uint32_t v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------
+// T fused steps of one environment per thread (pw_steps.cuh) + block-level counter flush.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void flush_counts(const StepCounts& c, const StepParams& p,
+                                             uint32_t* s_counters) {
+  // Launches without a counter vector (pw_step, pw_step_render) only report invalid actions, which
+  // are rare: one block-wide vote decides whether anything has to be reduced at all.
+  if (!p.counters && !__syncthreads_or(c.invalid != 0u)) return;
+  if (p.counters || p.status) {
+    const uint32_t c_term = warp_sum(c.terminated), c_moved = warp_sum(c.moved);
+    const uint32_t c_dg = warp_sum(c.dgoals), c_invalid = warp_sum(c.invalid);
+    if ((threadIdx.x & 31) == 0) {
+      if (c_term) atomicAdd(&s_counters[0], c_term);
+      if (c_moved) atomicAdd(&s_counters[1], c_moved);
+      if (c_dg) atomicAdd(&s_counters[2], c_dg);
+      if (c_invalid) atomicAdd(&s_counters[3], c_invalid);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      if (p.counters) {
+        const int64_t first = (int64_t)blockIdx.x * blockDim.x;
+        const int64_t rest = p.N - first;
+        const int64_t live = rest < (int64_t)blockDim.x ? rest : (int64_t)blockDim.x;
+        atomicAdd(&p.counters[0], (unsigned long long)(live > 0 ? live : 0) * (unsigned long long)p.T);
+        if (s_counters[0]) atomicAdd(&p.counters[1], (unsigned long long)s_counters[0]);
+        if (s_counters[1]) atomicAdd(&p.counters[2], (unsigned long long)s_counters[1]);
+        if (s_counters[2]) atomicAdd(&p.counters[3], (unsigned long long)s_counters[2]);
+      }
+      if (p.status && s_counters[3]) atomicAdd(&p.status[0], (unsigned long long)s_counters[3]);
+    }
+  }
+}
 
 __device__ __forceinline__ uint64_t splitmix64(uint64_t h) {
   h += 0x9e3779b97f4a7c15ull;
@@ -76,6 +122,7 @@ __device__ __forceinline__ void run_steps_sim(Sim& sim, const StepParams& p, int
   const uint8_t* __restrict__ actions = p.actions;
   float* __restrict__ reward = p.reward;
   uint8_t* __restrict__ terminated = p.terminated;
+  uint8_t* __restrict__ record = p.record;
   // Actions are independent of the state, so a whole group of kPrefetch steps is fetched one
   // group ahead (double buffering in registers): the loads of group g+1 are issued before the
   // steps of group g run, which covers the DRAM latency even at ~8 warps per scheduler.
@@ -102,8 +149,12 @@ __device__ __forceinline__ void run_steps_sim(Sim& sim, const StepParams& p, int
     c.dgoals += (uint32_t)max(dg, 0);
     if (bad_action) ++c.invalid;
     if (kLean) {
-      reward[off] = r;
-      terminated[off] = term ? 1 : 0;
+      if (record) {  // packed variant of the plain rollout
+        record[off] = (uint8_t)record_byte(dg, term, false);
+      } else {
+        reward[off] = r;
+        terminated[off] = term ? 1 : 0;
+      }
       off += n32;
     } else {
       const int64_t idx = (int64_t)t * N + e;
@@ -113,6 +164,7 @@ __device__ __forceinline__ void run_steps_sim(Sim& sim, const StepParams& p, int
       if (p.dgoals) p.dgoals[idx] = (int8_t)dg;
       if (p.terminated) p.terminated[idx] = term ? 1 : 0;
       if (p.truncated) p.truncated[idx] = trunc ? 1 : 0;
+      if (p.record) p.record[idx] = (uint8_t)record_byte(dg, term, trunc);
       if (p.moved) p.moved[idx] = moved;
       ret += r;
       if ((p.flags & kFlagAutoreset) && (term || trunc)) {
@@ -156,9 +208,12 @@ __device__ __forceinline__ void run_steps_thread(Env& env, const StepParams& p, 
   run_steps_sim<kLean>(sim, p, e, c);
 }
 
-// true when a launch has the "plain rollout" output shape (see run_steps_sim)
+// true when a launch has the "plain rollout" output shape (see run_steps_sim): reward + terminated
+// per step, or -- the packed variant -- one record byte per step, and nothing else
 inline bool is_lean(const StepParams& p) {
-  return p.reward && p.terminated && !p.dgoals && !p.truncated && !p.moved && !p.steps &&
+  const bool plain = p.reward && p.terminated && !p.record;
+  const bool packed = p.record && !p.reward && !p.terminated;
+  return (plain || packed) && !p.dgoals && !p.truncated && !p.moved && !p.steps &&
          !p.return_sum && p.flags == 0 && p.max_steps <= 0 &&
          (int64_t)p.T * p.N < ((int64_t)1 << 32);
 }

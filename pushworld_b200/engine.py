@@ -44,6 +44,36 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
 
+def _max_steps_arg(max_steps: Optional[int]) -> int:
+    """The C ABI's ``max_steps`` (<= 0 = no limit).  The reference computes ``truncated = steps >=
+    max_steps`` after incrementing ``steps`` (gym_env.py:201,223), so any limit <= 1 truncates
+    every step: ``max_steps=0`` (or a negative value) is passed on as 1, not as "no limit"."""
+    return 0 if max_steps is None else max(1, int(max_steps))
+
+
+_RECORD_LUT = None
+
+
+def record_to_outputs(record):
+    """Expands packed per-step records (``pw_rollout_packed``: uint8, bits 0..5 = delta_goals + 32,
+    bit 6 = truncated, bit 7 = terminated) into what ``PushWorldEnv.step`` returns
+    (gym_env.py:210-226): ``(reward float32, terminated uint8, truncated uint8, dgoals int8)``.
+    ``reward`` is bit-identical to the float32 rewards ``pw_rollout`` writes:
+    ``float32(10.0)`` if terminated else ``float32(float64(delta_goals) - 0.01)``.
+    Accepts a torch tensor (any device) or a numpy array; returns the same kind."""
+    global _RECORD_LUT
+    if _RECORD_LUT is None:
+        codes = np.arange(256)
+        dg = (codes & 0x3F).astype(np.float64) - 32.0
+        _RECORD_LUT = np.where(codes & 0x80, np.float32(10.0), (dg - 0.01).astype(np.float32)).astype(np.float32)
+    if isinstance(record, torch.Tensor):
+        lut = torch.from_numpy(_RECORD_LUT).to(record.device)
+        reward = lut[record.long()]
+        return (reward, (record >> 7), (record >> 6) & 1, ((record & 0x3F).to(torch.int16) - 32).to(torch.int8))
+    record = np.asarray(record, dtype=np.uint8)
+    return (_RECORD_LUT[record], record >> 7, (record >> 6) & 1, ((record & 0x3F).astype(np.int16) - 32).astype(np.int8))
+
+
 class Engine:
     """Immutable set of compiled puzzles resident on one CUDA device."""
 
@@ -168,7 +198,7 @@ class Engine:
             self._lib.pw_step(self._h, n, pid_ptr, pid, xy[0].data_ptr(), xy[1].data_ptr(), n,
                               action.data_ptr(), _ptr(out.reward), _ptr(out.dgoals),
                               _ptr(out.terminated), _ptr(out.truncated), _ptr(steps),
-                              int(max_steps or 0), _ptr(out.moved), self._stream())
+                              _max_steps_arg(max_steps), _ptr(out.moved), self._stream())
         )
         return out
 
@@ -197,7 +227,7 @@ class Engine:
         fn, handle, device = self._lib.pw_step, self._h, self.device
         head = (handle, n, pid_ptr, pid, xy[0].data_ptr(), xy[1].data_ptr(), n)
         tail = (_ptr(out.reward), _ptr(out.dgoals), _ptr(out.terminated), _ptr(out.truncated),
-                _ptr(steps), int(max_steps or 0), _ptr(out.moved))
+                _ptr(steps), _max_steps_arg(max_steps), _ptr(out.moved))
         current_stream = torch.cuda.current_stream
         shape = (n,)
 
@@ -240,9 +270,45 @@ class Engine:
         _lib.check(
             self._lib.pw_rollout(self._h, n, t, pid_ptr, pid, xy[0].data_ptr(), xy[1].data_ptr(), n,
                                  actions.data_ptr(), _ptr(reward), _ptr(dgoals), _ptr(terminated),
-                                 _ptr(truncated), _ptr(steps), int(max_steps or 0), _ptr(return_sum),
+                                 _ptr(truncated), _ptr(steps), _max_steps_arg(max_steps), _ptr(return_sum),
                                  _ptr(counters), _lib.PW_FLAG_AUTORESET if autoreset else 0,
                                  self._stream())
+        )
+
+    def rollout_packed(self, xy: torch.Tensor, puzzle: PuzzleSel, actions: torch.Tensor,
+                       record: torch.Tensor, steps: Optional[torch.Tensor] = None,
+                       max_steps: Optional[int] = None, return_sum: Optional[torch.Tensor] = None,
+                       counters: Optional[torch.Tensor] = None, autoreset: bool = False,
+                       episode: Optional[torch.Tensor] = None, seed: Optional[int] = None) -> None:
+        """``rollout`` writing ONE byte per environment step (``record`` uint8 ``[T, N]``, see
+        ``record_to_outputs``) instead of reward / terminated / truncated / dgoals arrays
+        (pw_rollout_packed).  With ``episode`` (int32 [N]) and ``seed`` the episode handling of
+        ``rollout_episodes`` is done on the device (``puzzle`` must then be the int32 [N] tensor)."""
+        n = self._chk_state(xy)
+        pid_ptr, pid = self._sel(puzzle, n)
+        if actions.dim() != 2 or actions.shape[1] != n:
+            raise ValueError(f"actions must have shape [T, {n}]")
+        t = actions.shape[0]
+        self._chk(actions, torch.uint8, (t, n), "actions")
+        self._chk(record, torch.uint8, (t, n), "record")
+        if steps is not None:
+            self._chk(steps, torch.int32, (n,), "steps")
+        if return_sum is not None:
+            self._chk(return_sum, torch.float32, (n,), "return_sum")
+        if counters is not None:
+            self._chk(counters, torch.int64, (4,), "counters")
+        flags = _lib.PW_FLAG_AUTORESET if autoreset else 0
+        if episode is not None:
+            if pid_ptr is None or steps is None or seed is None:
+                raise ValueError("episode handling needs a puzzle_id tensor, steps and a seed")
+            self._chk(episode, torch.int32, (n,), "episode")
+            flags |= _lib.PW_FLAG_RESAMPLE
+        _lib.check(
+            self._lib.pw_rollout_packed(self._h, n, t, pid_ptr, pid, xy[0].data_ptr(), xy[1].data_ptr(), n,
+                                        actions.data_ptr(), record.data_ptr(), _ptr(steps),
+                                        _max_steps_arg(max_steps), _ptr(return_sum), _ptr(counters),
+                                        flags, int(seed or 0) & (2**64 - 1), _ptr(episode),
+                                        self._stream())
         )
 
     def rollout_episodes(self, xy: torch.Tensor, puzzle_id: torch.Tensor, actions: torch.Tensor,
@@ -274,7 +340,7 @@ class Engine:
             self._lib.pw_rollout_episodes(self._h, n, t, puzzle_id.data_ptr(), xy[0].data_ptr(),
                                           xy[1].data_ptr(), n, actions.data_ptr(), _ptr(reward),
                                           _ptr(dgoals), _ptr(terminated), _ptr(truncated),
-                                          steps.data_ptr(), int(max_steps or 0), _ptr(return_sum),
+                                          steps.data_ptr(), _max_steps_arg(max_steps), _ptr(return_sum),
                                           _ptr(counters), int(seed) & (2**64 - 1), episode.data_ptr(),
                                           self._stream())
         )
@@ -439,11 +505,15 @@ class Engine:
             self._lib.pw_step_render(self._h, n, pid_ptr, pid, xy[0].data_ptr(), xy[1].data_ptr(),
                                      n, action.data_ptr(), _ptr(step_out.reward),
                                      _ptr(step_out.dgoals), _ptr(step_out.terminated),
-                                     _ptr(step_out.truncated), _ptr(steps), int(max_steps or 0),
+                                     _ptr(step_out.truncated), _ptr(steps), _max_steps_arg(max_steps),
                                      out.data_ptr(), code, pixels_per_cell, border_width, pad[0],
                                      pad[1], self._stream())
         )
         return out, step_out
+
+    def clear_status(self) -> None:
+        """Drops the invalid-action / overflow counts of earlier launches (asynchronous)."""
+        _lib.check(self._lib.pw_engine_clear_status(self._h, self._stream()))
 
     def poll_invalid_actions(self) -> int:
         """Number of out-of-range actions seen since the last poll (synchronises)."""

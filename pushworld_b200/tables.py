@@ -214,6 +214,8 @@ def build_blob(p: ParsedPuzzle) -> bytes:
         off = push_rows(_rows(cells, bh))
         if off > 0xFFFF:
             raise PuzzleLimitError("puzzle geometry exceeds the 16-bit row offset")
+        if bh > 255 or bw > MAX_WIDTH:
+            raise PuzzleLimitError(f"an object's bounding box exceeds {MAX_WIDTH} columns x 255 rows")
         desc.append(off | (bw << 16) | (bh << 24))
         desc.append((pos[0] & 0xFFFF) | ((pos[1] & 0xFFFF) << 16))
         desc.append(NO_GOAL if goal is None else (goal[0] & 0xFFFF) | ((goal[1] & 0xFFFF) << 16))

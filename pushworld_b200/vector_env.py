@@ -35,6 +35,8 @@ class RolloutOutput:
     truncated: Optional[torch.Tensor] = None
     return_sum: Optional[torch.Tensor] = None  # float32 [N]
     counters: Optional[torch.Tensor] = None  # int64 [4]
+    record: Optional[torch.Tensor] = None  # uint8 [T, N] packed records (rollout(packed=True))
+    global_counters: Optional[torch.Tensor] = None  # int64 [4]: `counters` summed over all ranks (shard=True)
 
 
 def load_puzzle_texts(puzzle_path: str) -> List[str]:
@@ -63,6 +65,12 @@ class PushWorldVectorEnv:
             (gym_env.py:57-64).
         observation: None (no rendering), "float32" (the reference observation) or "uint8".
         reuse_step_outputs: ``step`` returns the same output tensors on every call (see ``step``).
+        shard: one process per GPU (``torch.distributed``): ``num_envs`` / ``puzzle_ids`` describe
+            the GLOBAL batch and this process owns the contiguous slice
+            ``distributed.shard_range(num_envs, rank, world_size)`` of it (``shard_lo``, ``shard_hi``;
+            ``num_envs`` becomes the local count, ``global_num_envs`` the total).  Environments
+            never interact, so nothing is exchanged except ONE all-reduce of the int64[4] counter
+            vector per ``rollout`` (``RolloutOutput.global_counters``), SURVEY.md 8e.
     """
 
     def __init__(
@@ -78,6 +86,8 @@ class PushWorldVectorEnv:
         device: Union[int, str, torch.device, None] = None,
         autoreset: bool = False,
         reuse_step_outputs: bool = False,
+        shard: bool = False,
+        check_rollout_actions: bool = False,
     ) -> None:
         texts = load_puzzle_texts(puzzles) if isinstance(puzzles, str) else list(puzzles)
         if len(texts) == 0:
@@ -90,7 +100,16 @@ class PushWorldVectorEnv:
             raise ValueError("observation must be None, 'float32' or 'uint8'")
         self.engine = Engine(texts, device=device)
         self.device = self.engine.device
-        self.num_envs = int(num_envs)
+        self.global_num_envs = int(num_envs)
+        self.sharded = bool(shard)
+        if shard:
+            from . import distributed as _dist
+
+            rank, world = _dist.rank_and_world()
+            self.shard_lo, self.shard_hi = _dist.shard_range(self.global_num_envs, rank, world)
+        else:
+            self.shard_lo, self.shard_hi = 0, self.global_num_envs
+        self.num_envs = self.shard_hi - self.shard_lo
         self.max_steps = max_steps
         self.border_width = border_width
         self.pixels_per_cell = pixels_per_cell
@@ -99,6 +118,10 @@ class PushWorldVectorEnv:
         # per-step loops: bind the native call's arguments once and write every step's outputs into
         # the same tensors (Engine.prepare_step: ~2x fewer microseconds per step() call)
         self.reuse_step_outputs = reuse_step_outputs
+        # rollouts count out-of-range actions as no-ops; True = poll after every rollout (this
+        # synchronises) and raise the reference's ValueError like step() does
+        self.check_rollout_actions = check_rollout_actions
+        self._status_dirty = False  # a rollout may have left counts in the engine's status block
 
         max_h, max_w = self.engine.max_height, self.engine.max_width
         if standard_padding:  # gym_env.py:86-105
@@ -112,22 +135,19 @@ class PushWorldVectorEnv:
         self.pad_cells = (max_h, max_w)
 
         n = self.num_envs
+        lo, hi = self.shard_lo, self.shard_hi
         if isinstance(puzzle_ids, int):
             self._uniform: Optional[int] = puzzle_ids
             self.puzzle_id = None
-            self.env_index = torch.arange(n, device=self.device)
+            self.env_index = torch.arange(lo, hi, device=self.device)
         else:
             self._uniform = None
-            if puzzle_ids is None:
-                ids = torch.arange(n, dtype=torch.int64) % self.engine.num_puzzles
-                order = torch.argsort(ids, stable=True)
-                self.env_index = order.to(self.device)
-                ids = ids[order]
-            else:
-                ids = torch.as_tensor(puzzle_ids, dtype=torch.int64).cpu()
-                if ids.numel() != n:
-                    raise ValueError("puzzle_ids must have num_envs entries")
-                self.env_index = torch.arange(n, device=self.device)
+            from . import distributed as _dist
+
+            rank, world = _dist.rank_and_world() if shard else (0, 1)
+            ids, env_index, _, _ = _dist.shard_puzzle_ids(self.global_num_envs, self.engine.num_puzzles,
+                                                          puzzle_ids, rank, world)
+            self.env_index = env_index.to(self.device)
             if n and (ids.min() < 0 or ids.max() >= self.engine.num_puzzles):
                 raise ValueError("puzzle id out of range")
             self.puzzle_id = ids.to(torch.int32).to(self.device)
@@ -185,6 +205,10 @@ class PushWorldVectorEnv:
         are REUSED by the next ``step`` call (clone them to keep them)."""
         self._require_reset()
         actions = self._as_actions(actions, (self.num_envs,))
+        if check_actions and self._status_dirty:
+            # invalid actions an earlier (unchecked) rollout counted must not fail THIS step
+            self.engine.clear_status()
+            self._status_dirty = False
         if self.observation is None and not self.reuse_step_outputs:
             out = self.engine.step(self.xy, self._sel, actions, steps=self.steps,
                                    max_steps=self.max_steps)
@@ -219,7 +243,7 @@ class PushWorldVectorEnv:
 
     def rollout(self, actions: torch.Tensor, want_reward: bool = True, want_terminated: bool = True,
                 want_dgoals: bool = False, want_truncated: bool = False, want_return: bool = False,
-                out: Optional[RolloutOutput] = None) -> RolloutOutput:
+                out: Optional[RolloutOutput] = None, packed: bool = False) -> RolloutOutput:
         """T fused steps in one launch; ``actions`` uint8 ``[T, N]`` on the device.  With only
         reward + terminated requested and no ``max_steps`` / ``autoreset`` the engine runs its
         lean rollout loop (every optional output compiled out)."""
@@ -229,6 +253,11 @@ class PushWorldVectorEnv:
         actions = self._as_actions(actions, (actions.shape[0], self.num_envs))
         t, n = actions.shape
         dev = self.device
+        if out is None and packed:
+            out = RolloutOutput(reward=None, terminated=None,
+                                record=torch.empty((t, n), dtype=torch.uint8, device=dev),
+                                return_sum=torch.zeros(n, dtype=torch.float32, device=dev) if want_return else None,
+                                counters=torch.zeros(4, dtype=torch.int64, device=dev))
         if out is None:
             out = RolloutOutput(
                 reward=torch.empty((t, n), dtype=torch.float32, device=dev) if want_reward else None,
@@ -239,14 +268,40 @@ class PushWorldVectorEnv:
                 counters=torch.zeros(4, dtype=torch.int64, device=dev),
             )
         track_steps = self.max_steps is not None or self.autoreset
-        self.engine.rollout(self.xy, self._sel, actions, reward=out.reward, terminated=out.terminated,
-                            dgoals=out.dgoals, truncated=out.truncated,
-                            steps=self.steps if track_steps else None,
-                            max_steps=self.max_steps, return_sum=out.return_sum,
-                            counters=out.counters, autoreset=self.autoreset)
+        if out.record is not None:
+            self.engine.rollout_packed(self.xy, self._sel, actions, out.record,
+                                       steps=self.steps if track_steps else None,
+                                       max_steps=self.max_steps, return_sum=out.return_sum,
+                                       counters=out.counters, autoreset=self.autoreset)
+        else:
+            self.engine.rollout(self.xy, self._sel, actions, reward=out.reward, terminated=out.terminated,
+                                dgoals=out.dgoals, truncated=out.truncated,
+                                steps=self.steps if track_steps else None,
+                                max_steps=self.max_steps, return_sum=out.return_sum,
+                                counters=out.counters, autoreset=self.autoreset)
         if not track_steps:
             self.steps += actions.shape[0]
+        self._poll_after_rollout()
+        if self.sharded and out.counters is not None:
+            # the path's single collective: one all-reduce (sum) of int64[4] per rollout
+            from . import distributed as _dist
+
+            if out.global_counters is None:
+                out.global_counters = torch.empty_like(out.counters)
+            out.global_counters.copy_(out.counters)
+            _dist.allreduce_counters(out.global_counters)
         return out
+
+    def _poll_after_rollout(self) -> None:
+        """Rollouts treat out-of-range actions as counted no-ops (the launch is asynchronous); with
+        ``check_rollout_actions`` set the count is polled here (synchronises) and raises the
+        reference's ValueError (gym_env.py:195-196).  Either way the count never leaks into a
+        later ``step`` call: ``step`` only looks at actions counted by its own launch."""
+        if self.check_rollout_actions:
+            if self.engine.poll_invalid_actions():
+                raise ValueError("The provided action is not in the action space.")
+        else:
+            self._status_dirty = True
 
     # ------------------------------------------------------------------ host-buffer entry point
     def rollout_host(self, actions: torch.Tensor, reward: torch.Tensor, terminated: torch.Tensor,
@@ -262,6 +317,22 @@ class PushWorldVectorEnv:
         assert actions.is_pinned() and reward.is_pinned() and terminated.is_pinned()
         pipe = self._host_pipe(chunk_steps)
         pipe.run(self, actions, reward, terminated)
+        self._poll_after_rollout()
+
+    def rollout_host_packed(self, actions: torch.Tensor, record: torch.Tensor,
+                            chunk_steps: int = 64) -> None:
+        """``rollout_host`` with ONE byte out per environment step: ``record`` (uint8 [T, N],
+        pinned host memory) receives the packed per-step records of ``pw_rollout_packed``
+        (delta_goals, terminated, truncated); ``engine.record_to_outputs(record)`` expands them
+        to the float32 rewards / flags ``rollout_host`` returns, bit for bit.  PCIe traffic is
+        1 byte in + 1 byte out per environment step instead of 1 + 5."""
+        self._require_reset()
+        t, n = actions.shape
+        assert n == self.num_envs and record.shape == (t, n) and record.dtype == torch.uint8
+        assert actions.is_pinned() and record.is_pinned()
+        pipe = self._host_pipe(chunk_steps)
+        pipe.run(self, actions, None, None, record=record)
+        self._poll_after_rollout()
 
     def rollout_host_returns(self, actions: torch.Tensor, returns: torch.Tensor,
                              n_terminated: torch.Tensor, chunk_steps: int = 64) -> None:
@@ -277,6 +348,7 @@ class PushWorldVectorEnv:
         assert actions.is_pinned() and returns.is_pinned() and n_terminated.is_pinned()
         pipe = self._host_pipe(chunk_steps)
         pipe.run_returns(self, actions, returns, n_terminated)
+        self._poll_after_rollout()
 
     def _host_pipe(self, chunk_steps: int):
         pipe = getattr(self, "_pipe", None)
@@ -296,13 +368,32 @@ class _HostPipe:
         self.s_in = torch.cuda.Stream(device)
         self.s_run = torch.cuda.Stream(device)
         self.s_out = torch.cuda.Stream(device)
-        mk = lambda dt: [torch.empty((chunk, n), dtype=dt, device=device) for _ in range(self.DEPTH)]
-        self.d_act, self.d_rew, self.d_term = mk(torch.uint8), mk(torch.float32), mk(torch.uint8)
+        self._mk = lambda dt: [torch.empty((chunk, n), dtype=dt, device=device) for _ in range(self.DEPTH)]
+        self.d_act = self._mk(torch.uint8)
+        self._d_rew = self._d_term = self._d_rec = None  # allocated by the first run that needs them
         self.ev_in = [torch.cuda.Event() for _ in range(self.DEPTH)]
         self.ev_run = [torch.cuda.Event() for _ in range(self.DEPTH)]
         self.ev_out = [torch.cuda.Event() for _ in range(self.DEPTH)]
 
-    def run(self, env: "PushWorldVectorEnv", actions, reward, terminated) -> None:
+    @property
+    def d_rew(self):
+        if self._d_rew is None:
+            self._d_rew = self._mk(torch.float32)
+        return self._d_rew
+
+    @property
+    def d_term(self):
+        if self._d_term is None:
+            self._d_term = self._mk(torch.uint8)
+        return self._d_term
+
+    @property
+    def d_rec(self):
+        if self._d_rec is None:
+            self._d_rec = self._mk(torch.uint8)
+        return self._d_rec
+
+    def run(self, env: "PushWorldVectorEnv", actions, reward, terminated, record=None) -> None:
         t = actions.shape[0]
         cur = torch.cuda.current_stream(env.device)
         for s in (self.s_in, self.s_run, self.s_out):
@@ -322,16 +413,24 @@ class _HostPipe:
                 if k >= self.DEPTH:
                     self.s_run.wait_event(self.ev_out[b])  # outputs of chunk k-DEPTH copied out
                 track = env.max_steps is not None or env.autoreset
-                env.engine.rollout(env.xy, env._sel, self.d_act[b][:m], reward=self.d_rew[b][:m],
-                                   terminated=self.d_term[b][:m], steps=env.steps if track else None,
-                                   max_steps=env.max_steps, autoreset=env.autoreset)
+                if record is not None:
+                    env.engine.rollout_packed(env.xy, env._sel, self.d_act[b][:m], self.d_rec[b][:m],
+                                              steps=env.steps if track else None,
+                                              max_steps=env.max_steps, autoreset=env.autoreset)
+                else:
+                    env.engine.rollout(env.xy, env._sel, self.d_act[b][:m], reward=self.d_rew[b][:m],
+                                       terminated=self.d_term[b][:m], steps=env.steps if track else None,
+                                       max_steps=env.max_steps, autoreset=env.autoreset)
                 if not track:
                     env.steps += m
                 self.ev_run[b].record(self.s_run)
             with torch.cuda.stream(self.s_out):
                 self.s_out.wait_event(self.ev_run[b])
-                reward[lo:hi].copy_(self.d_rew[b][:m], non_blocking=True)
-                terminated[lo:hi].copy_(self.d_term[b][:m], non_blocking=True)
+                if record is not None:
+                    record[lo:hi].copy_(self.d_rec[b][:m], non_blocking=True)
+                else:
+                    reward[lo:hi].copy_(self.d_rew[b][:m], non_blocking=True)
+                    terminated[lo:hi].copy_(self.d_term[b][:m], non_blocking=True)
                 self.ev_out[b].record(self.s_out)
         cur.wait_stream(self.s_out)
         cur.wait_stream(self.s_run)

@@ -43,6 +43,24 @@ def _worker(rank, world, port, total_envs, out):
     distributed.allreduce_counters(counters)
     slowest = distributed.max_over_ranks(1.0 + rank)
     distributed.barrier()
+    assert distributed.rank_and_world() == (rank, world)
+    # the sharded vector environment's layout: every rank's slice of the global batch
+    mine = []
+    for ids in (None, [(7 * e) % 5 for e in range(total_envs)]):
+        got_ids, env_index, slo, shi = distributed.shard_puzzle_ids(total_envs, 5, ids, rank, world)
+        assert (slo, shi) == (lo, hi) and len(got_ids) == hi - lo == len(env_index)
+        mine.append((got_ids.tolist(), env_index.tolist()))
+    gathered = [None] * world
+    dist.all_gather_object(gathered, mine)
+    if rank == 0:
+        for case, ids in enumerate((None, [(7 * e) % 5 for e in range(total_envs)])):
+            all_ids = sum((g[case][0] for g in gathered), [])
+            all_index = sum((g[case][1] for g in gathered), [])
+            assert sorted(all_index) == list(range(total_envs))  # every environment exactly once
+            want = [e % 5 for e in range(total_envs)] if ids is None else ids
+            assert all(all_ids[k] == want[all_index[k]] for k in range(total_envs))
+            if ids is None:
+                assert all_ids == sorted(all_ids)  # grouped by puzzle before the cut
     if rank == 0:
         out.put((counters.tolist(), slowest))
     dist.destroy_process_group()

@@ -54,6 +54,8 @@ def test_table_header_fields(golden):
         ("a g1\n. m0\n", AssertionError),  # goal without movable, puzzle.py:230-232
         ("a .\n. .\n\n", ValueError),  # trailing blank line = ragged row
         (" ".join(["."] * 63 + ["a"]) + "\n", ValueError),  # 66 columns > PW_MAX_WIDTH
+        # a movable whose bounding box spans 300 rows: the 8-bit height field cannot hold it
+        ("m1 a\n" + ". .\n" * 298 + "m1 .\n", ValueError),
     ],
 )
 def test_compile_errors(text, exc):
@@ -68,3 +70,24 @@ def test_line_endings_and_case():
     assert _lib.compile_puzzle_text("A M0 .\r\n. . G0\r\n") == ref
     assert _lib.compile_puzzle_text("a m0 .\n. . g0") == ref
     assert _lib.compile_puzzle_text("  a\tm0   .  \n .  . g0 \n") == ref
+
+
+def test_record_expansion_matches_the_reference_reward_arithmetic():
+    """The packed per-step record (pw_rollout_packed) expands to the float32 image of the python
+    float the reference computes (gym_env.py:212-221)."""
+    import numpy as np
+
+    from pushworld_b200.engine import record_to_outputs
+
+    codes = np.arange(256, dtype=np.uint8)
+    reward, term, trunc, dg = record_to_outputs(codes)
+    for c in range(256):
+        d = (c & 0x3F) - 32
+        want = 10.0 if c & 0x80 else float(d) - 0.01
+        assert reward[c] == np.float32(want) and term[c] == (c >> 7) and trunc[c] == ((c >> 6) & 1)
+        assert dg[c] == d
+    import torch
+
+    r_t, t_t, tr_t, dg_t = record_to_outputs(torch.from_numpy(codes))
+    assert np.array_equal(r_t.numpy(), reward) and np.array_equal(dg_t.numpy(), dg)
+    assert np.array_equal(t_t.numpy(), term) and np.array_equal(tr_t.numpy(), trunc)
