@@ -16,7 +16,7 @@ pytestmark = pytest.mark.gpu
 
 import c_oracle  # noqa: E402
 import pushworld_oracle as po  # noqa: E402
-from oracle_batch import OracleSet  # noqa: E402
+from tests.oracle_batch import OracleSet  # noqa: E402
 
 
 def _actions(T, n, seed):
