@@ -55,6 +55,11 @@ struct OccEnv : EnvBase<GlobalTable> {
   int ax, ay;
   int* sx;  // object j >= 1 at sx[(j - 1) * kOccBlock]
   int* sy;
+  // masks: sy holds, instead of y, the ROW MASK of the object -- bit r set for every grid row
+  // y .. y + h - 1 it spans (y = lowest set bit): the candidate filter of closure_occ.  Only for
+  // environments whose objects all lie inside a grid of at most 32 rows (see build_occupancy).
+  bool masks = false;
+  __device__ __forceinline__ uint32_t rowmask(int j) const { return (uint32_t)sy[(j - 1) * kOccBlock]; }
   __device__ __forceinline__ void init(GlobalTable table, int* x_col, int* y_col) {
     this->init_header(table);
     sx = x_col;
@@ -73,14 +78,18 @@ struct OccEnv : EnvBase<GlobalTable> {
     y[e] = ay;
     for (int j = 1; j < this->n_; ++j) {
       x[j * stride + e] = sx[(j - 1) * kOccBlock];
-      y[j * stride + e] = sy[(j - 1) * kOccBlock];
+      y[j * stride + e] = this->y(j);
     }
   }
   __device__ __forceinline__ uint32_t desc(int j) const { return this->table_desc(j, 0); }
   __device__ __forceinline__ uint32_t desc_dyn(int j) const { return this->table_desc(j, 0); }
   // j >= 1 in every loop over pushees / goal objects; index 0 only through x(0) / x_dyn(pusher)
   __device__ __forceinline__ int x(int j) const { return j == 0 ? ax : sx[(j - 1) * kOccBlock]; }
-  __device__ __forceinline__ int y(int j) const { return j == 0 ? ay : sy[(j - 1) * kOccBlock]; }
+  __device__ __forceinline__ int y(int j) const {
+    if (j == 0) return ay;
+    const int v = sy[(j - 1) * kOccBlock];
+    return masks ? __ffs(v) - 1 : v;
+  }
   __device__ __forceinline__ int x_dyn(int j) const { return x(j); }
   __device__ __forceinline__ int y_dyn(int j) const { return y(j); }
   __device__ __forceinline__ int goal_x(int k) const { return lo16(this->table_desc(k + 1, 2)); }
@@ -95,31 +104,111 @@ struct OccEnv : EnvBase<GlobalTable> {
       const int j = __ffs((int)mask) - 1;
       mask &= mask - 1;
       if (dx) sx[(j - 1) * kOccBlock] += dx;
-      if (dy) sy[(j - 1) * kOccBlock] += dy;
+      if (dy) sy[(j - 1) * kOccBlock] += dy;  // (plain positions: the generic closure never runs with masks)
     }
   }
 };
 
-// Rebuilds the occupancy rows of this thread's environment from the positions of objects 1..n-1.
-// occ: &s_occ[0][tid], row r at occ[r * kOccBlock].  Cells outside the grid are dropped: the
-// fast path is only taken when the moved agent lies inside the grid.
-template <class Env>
-__device__ __forceinline__ void rebuild_occupancy(const Env& env, uint32_t* occ, int H) {
+// Builds the occupancy rows of this thread's environment from the positions of objects 1..n-1
+// (occ: &s_occ[0][tid], row r at occ[r * kOccBlock]) and reports whether the environment can use
+// them: every movable inside the grid, no two movables overlapping, none overlapping a wall.  Such a
+// state stays that way: a movable that does not overlap a wall is stopped by the border walls
+// (puzzle.py:160-168, 284-293), and a movable that would be moved onto another one pushes it
+// (:359-382), so the occupancy can be maintained incrementally.  Every other environment runs the
+// table rule on every step.
+__device__ __forceinline__ bool build_occupancy(const OccEnv& env, uint32_t* occ, int W, int H) {
   for (int r = 0; r < H; ++r) occ[r * kOccBlock] = 0u;
-  const int n = env.n();
+  const int n = env.n(), wall_off = env.wall_off();
+  bool ok = true;
   for (int j = 1; j < n; ++j) {
     const uint32_t d = env.desc(j);
     const int x = env.x(j), y = env.y(j);
-    const int h = desc_h(d), o = desc_off(d);
-    if (x <= -32 || x >= 32) continue;
+    const int w = desc_w(d), h = desc_h(d), o = desc_off(d);
+    if (x < 0 || y < 0 || x + w > W || y + h > H) {
+      ok = false;
+      continue;
+    }
     for (int r = 0; r < h; ++r) {
-      const int yy = y + r;
-      if ((unsigned)yy >= (unsigned)H) continue;
-      const uint64_t row = env.row(o + r);
-      const uint32_t bits = x >= 0 ? (uint32_t)(row << x) : (uint32_t)(row >> (-x));
-      occ[yy * kOccBlock] |= bits;
+      const uint64_t bits = env.row(o + r) << x;
+      const uint32_t have = occ[(y + r) * kOccBlock];
+      ok = ok && (have & (uint32_t)bits) == 0u && (env.row(wall_off + y + r) & bits) == 0ull;
+      occ[(y + r) * kOccBlock] = have | (uint32_t)bits;
     }
   }
+  return ok;
+}
+
+// The push closure of one step (puzzle.py:359-394) for an environment with occupancy rows:
+//   * a pusher whose displaced cells touch no occupied cell pushes nothing (puzzle.py:567-593 needs
+//     the moved pusher to overlap the pushee), so its scan over the other objects is skipped;
+//   * otherwise only objects that span one of the rows with a hit are tested, with the exact
+//     collision-table look-ups of pw_fast.cuh (tab_pushes, tab_wall);
+//   * objects that join the pushed set leave the occupancy and re-enter it displaced (or where they
+//     were, on transitive stopping, puzzle.py:376-379).
+// Returns the moved-object mask (0 = nothing moves); positions and occupancy are updated.
+__device__ __forceinline__ uint32_t closure_occ(OccEnv& env, uint32_t* occ, uint32_t a, int H, uint32_t nn1) {
+  const int n = env.n();
+  const int dx = action_dx((int)a), dy = action_dy((int)a);
+  // (the caller has already found that the walls do not stop the agent, puzzle.py:353-354)
+  uint32_t pushed = 1u, frontier = 1u;
+  bool stop = false;
+  while (frontier) {
+    const int i = __ffs((int)frontier) - 1;
+    frontier &= frontier - 1;
+    const uint32_t di = env.desc(i);
+    const int xi = env.x(i), yi = env.y(i);
+    const int hi = desc_h(di), oi = desc_off(di);
+    const int xm = xi + dx, ym = yi + dy;
+    uint32_t hitrows = 0u;
+    if (xm > -64 && xm < 32) {  // (only the agent can be outside the grid)
+      for (int r = 0; r < hi; ++r) {
+        const int yy = ym + r;
+        if ((unsigned)yy >= (unsigned)H) continue;
+        const uint64_t row = env.row(oi + r);
+        const uint32_t bits = xm >= 0 ? (uint32_t)(row << xm) : (uint32_t)(row >> (-xm));
+        hitrows |= (bits & occ[yy * kOccBlock]) ? (1u << yy) : 0u;
+      }
+    }
+    if (hitrows == 0u) continue;
+    uint32_t cand = 0u;
+#pragma unroll 4
+    for (int j = 1; j < n; ++j) cand |= (env.rowmask(j) & hitrows) ? (1u << j) : 0u;
+    cand &= ~pushed;
+    while (cand) {
+      const int j = __ffs((int)cand) - 1;
+      cand &= cand - 1;
+      const int xj = env.x(j), yj = env.y(j);
+      if (!tab_pushes(env, 1u + (uint32_t)(i * n + j), a, xj - xi, yj - yi)) continue;
+      if (tab_wall(env, nn1, (uint32_t)j, a, xj, yj)) {  // transitive stopping
+        stop = true;
+        break;
+      }
+      pushed |= 1u << j;
+      frontier |= 1u << j;
+      const uint32_t dj = env.desc(j);
+      const int hj = desc_h(dj), oj = desc_off(dj);
+      for (int r = 0; r < hj; ++r) occ[(yj + r) * kOccBlock] &= ~(uint32_t)(env.row(oj + r) << xj);
+    }
+    if (stop) break;
+  }
+  uint32_t rest = pushed & ~1u;
+  while (rest) {
+    const int j = __ffs((int)rest) - 1;
+    rest &= rest - 1;
+    const uint32_t dj = env.desc(j);
+    const int hj = desc_h(dj), oj = desc_off(dj);
+    const int nx = env.x(j) + (stop ? 0 : dx), ny = env.y(j) + (stop ? 0 : dy);
+    for (int r = 0; r < hj; ++r) occ[(ny + r) * kOccBlock] |= (uint32_t)(env.row(oj + r) << nx);
+    if (!stop) {
+      env.sx[(j - 1) * kOccBlock] = nx;
+      const uint32_t m = env.rowmask(j);
+      env.sy[(j - 1) * kOccBlock] = (int)(dy > 0 ? m << 1 : (dy < 0 ? m >> 1 : m));
+    }
+  }
+  if (stop) return 0u;
+  env.ax += dx;
+  env.ay += dy;
+  return pushed;
 }
 
 template <bool kPacked>
@@ -162,9 +251,16 @@ __global__ void __launch_bounds__(kOccBlock)
     const uint32_t d0 = env.desc(0);
     const int h0 = desc_h(d0), o0 = desc_off(d0);
     const bool agent_1x1 = (d0 >> 16) == 0x0101u;
-    const bool small = W <= 32 && H <= kOccRows;
     uint32_t* const occ = s_occ + tid;
-    if (small) rebuild_occupancy(env, occ, H);
+    // occupancy rows: puzzles of at most 32 x 32 cells whose state is regular (build_occupancy)
+    const bool fast_ok = W <= 32 && H <= kOccRows && build_occupancy(env, occ, W, H);
+    if (fast_ok) {  // rows instead of y for objects 1 .. n-1 (see OccEnv::masks)
+      for (int j = 1; j < n; ++j) {
+        const int h = desc_h(env.desc(j));
+        env.sy[(j - 1) * kOccBlock] = (int)((0xffffffffu >> (32 - h)) << env.sy[(j - 1) * kOccBlock]);
+      }
+      env.masks = true;
+    }
     int& ax = env.ax;
     int& ay = env.ay;
     int ach = achieved_goals(env);
@@ -228,40 +324,36 @@ __global__ void __launch_bounds__(kOccBlock)
     while (base < n_tiles) {
       const int lim = min(T, 32 * (base + 2));
       if (!parked && t < lim) {
-        // ---- fast attempt -------------------------------------------------------------------
+        // ---- fast attempt (branch-free: the lanes of a warp stay together) ---------------------
         const uint32_t a = act_ring[(uint32_t)((t >> 5) % kActTiles) * kTileBytes + ((uint32_t)(t & 31) << 5) + lane];
         const bool valid = a <= 3u;
         const uint32_t sel = a * 0x1111u + 0x8880u;  // byte a, sign extended
         const int dx = (int)__byte_perm(kDxBytes, 0u, sel), dy = (int)__byte_perm(kDyBytes, 0u, sel);
         // walls (puzzle.py:353-354): one bit of the agent's collision table
-        bool stopped = false;
-        if ((uint32_t)ax <= aw_xmax && (uint32_t)ay <= aw_ymax) {
-          const uint32_t idx = ((((uint32_t)ay * aw_w + (uint32_t)ax) << 2) | (a & 3u));
-          stopped = tab_bit(env.fast32(aw_word0 + (idx >> 5)), idx);
-        }
+        const bool here = (uint32_t)ax <= aw_xmax && (uint32_t)ay <= aw_ymax;
+        const uint32_t idx = here ? ((((uint32_t)ay * aw_w + (uint32_t)ax) << 2) | (a & 3u)) : 0u;
+        const bool stopped = here && tab_bit(env.fast32(aw_word0 + (idx >> 5)), idx);
         const int x = ax + dx, y = ay + dy;
-        bool need_closure = !small || (uint32_t)x > aw_xmax || (uint32_t)y > aw_ymax;
-        if (!need_closure) {
-          // does the moved agent touch a movable?  (rows y .. y + h0 - 1 are inside the grid)
-          if (agent_1x1) {
-            need_closure = ((occ[y * kOccBlock] >> x) & 1u) != 0u;
-          } else {
-            uint32_t hit = 0;
+        // does the moved agent (inside the grid: rows y .. y + h0 - 1 exist) touch a movable?
+        const bool there = fast_ok && (uint32_t)x <= aw_xmax && (uint32_t)y <= aw_ymax;
+        uint32_t hit;
+        if (agent_1x1) {
+          hit = (occ[(there ? y : 0) * kOccBlock] >> (x & 31)) & 1u;
+        } else {
+          hit = 0u;
+          if (there)
             for (int r = 0; r < h0; ++r) hit |= (uint32_t)(env.row(o0 + r) << x) & occ[(y + r) * kOccBlock];
-            need_closure = hit != 0u;
-          }
         }
-        if (!valid || stopped) {
-          n_invalid += valid ? 0u : 1u;
-        } else if (need_closure) {
+        const bool go = valid && !stopped;
+        const bool free_move = go && there && hit == 0u;
+        n_invalid += valid ? 0u : 1u;
+        n_moved += free_move ? 1u : 0u;
+        ax = free_move ? x : ax;
+        ay = free_move ? y : ay;
+        if (go && !free_move) {
           parked = true;
           parked_action = a;
         } else {
-          ax = x;
-          ay = y;
-          ++n_moved;
-        }
-        if (!parked) {
           out_ring[((uint32_t)(t & 63) << 5) + lane] = (uint8_t)code_idle;
           n_term += code_idle >> 7;
           ++t;
@@ -272,15 +364,17 @@ __global__ void __launch_bounds__(kOccBlock)
       if (m_parked != 0u && (__popc(m_parked) >= batch || m_ready == 0u)) {
         if (parked) {
           // ---- the exact closure (puzzle.py:359-394 on the collision tables), parked lanes only
-          const uint32_t pushed = pushed_set_tab(env, (int)parked_action);
+          uint32_t pushed;
+          if (fast_ok) {
+            pushed = closure_occ(env, occ, parked_action, H, nn1);
+          } else {
+            pushed = pushed_set_tab(env, (int)parked_action);
+            if (pushed) env.translate(pushed, action_dx((int)parked_action), action_dy((int)parked_action));
+          }
           int now = ach;
           if (pushed) {
-            env.translate(pushed, action_dx((int)parked_action), action_dy((int)parked_action));
             ++n_moved;
-            if (pushed & ~1u) {
-              now = achieved_goals(env);
-              if (small) rebuild_occupancy(env, occ, H);
-            }
+            if (pushed & ~1u) now = achieved_goals(env);
           }
           const int dg = now - ach;
           ach = now;

@@ -60,7 +60,7 @@ def test_config2_every_column_matches_the_c_oracle():
     assert np.array_equal(term.cpu().numpy(), o_term)
     got = xy.cpu().numpy()
     assert np.array_equal(got[0], ox) and np.array_equal(got[1], oy)
-    assert o_term.any() and (o_rew == np.float32(0.99)).any()  # the sample does reach the goal
+    assert o_term.any() and (o_rew == np.float32(10.0)).any()  # the sample does reach the goal
 
 
 @pytest.mark.parametrize("order", ["grouped", "interleaved"])

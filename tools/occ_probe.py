@@ -43,6 +43,7 @@ def main():
     ap.add_argument("--steps", type=int, default=256)
     ap.add_argument("--envs", type=int, default=1 << 18)
     ap.add_argument("--out", default="")
+    ap.add_argument("--batches", type=int, nargs="*", default=[4, 8, 12, 16, 24])
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     keys = data.benchmark_keys()
@@ -57,7 +58,7 @@ def main():
     term = torch.empty((T, n), dtype=torch.uint8, device=dev)
     xy = eng.new_state(n)
     results = []
-    variants = [("occ batch=%d" % b, {"PW_OCC_BATCH": str(b)}) for b in (1, 4, 8, 12, 16, 24, 32)]
+    variants = [("occ batch=%d" % b, {"PW_OCC_BATCH": str(b)}) for b in args.batches]
     variants += [("scan every step (round 1)", {"PW_NO_OCC": "1"}), ("warp per environment", {"PW_WARP_PER_ENV": "1"})]
     for layout, pid in layouts.items():
         ref = None
