@@ -305,7 +305,7 @@ def run_configs(rank, world, dev, peak, sampler, reps=5):
                f"cfg3: 2^18 envs over all {len(keys)} benchmark puzzles "
                f"({'grouped by puzzle' if ids is None else 'env e -> puzzle e mod 223'}), T=1024, "
                "reward f32 + terminated u8 per step",
-               "k_rollout_occ (general rule: occupancy reject + batched push closure)",
+               "k_rollout_mask (general rule: bounding-box mask prefilter + collision-table look-ups)",
                n_total * T, ms, 6.0 + 16.0 * n_obj / T, 16.0 * n_obj + 6.0, {"unit": "env-steps"})
         del env, actions, ro
     torch.cuda.empty_cache()

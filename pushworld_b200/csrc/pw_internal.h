@@ -30,7 +30,8 @@ struct StepParams {
   int32_t board_bits;   // bits puzzle_uniform needs in board form if it is regular, else 1 << 30
   int32_t ring_goals;   // > 0: puzzle_uniform fits ring boards (pw_board.cuh), value = its goal count
   int32_t lean_tiles;   // set by launch_steps: lean shape, N % 32 == 0, 16-byte aligned actions
-  int32_t occ_batch;    // set by launch_rollout_occ: parked lanes that trigger a closure pass
+  int32_t occ_batch;         // set by launch_rollout_occ: parked lanes that trigger a closure pass (run-ahead kernel)
+  int32_t occ_warp_closure;  // set by launch_rollout_occ (pw_occ.cu): closure per warp instead of per thread
   int32_t episode_tiles;  // set by launch_steps: pw_rollout_episodes with reward + terminated (+ truncated), whole warps
   const BoardStaticPod* board_static;  // device; entry of puzzle_uniform (valid if board_bits <= 64)
   int32_t* x;

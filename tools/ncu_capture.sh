@@ -11,4 +11,5 @@ ncu --set full --clock-control none --import-source on -k "regex:${kernel}" -s "
     -o "${rep%.ncu-rep}" "$@" > "gpurun_out/${tag}.log" 2>&1
 ncu -i "${rep}" --page raw --csv 2>/dev/null | gzip -9 > "gpurun_out/${tag}.raw.csv.gz"
 ncu -i "${rep}" --page source --csv 2>/dev/null | gzip -9 > "gpurun_out/${tag}.source.csv.gz"
+ncu -i "${rep}" --page source --print-source cuda --csv 2>/dev/null | gzip -9 > "gpurun_out/${tag}.cuda.csv.gz"
 ls -la "gpurun_out/${tag}".*

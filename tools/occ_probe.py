@@ -3,7 +3,7 @@
 
     python tools/occ_probe.py [--steps 256] [--out gpurun_out/occ_probe.json]
 
-* k_rollout_occ (occupancy reject + batched closure) at several batch thresholds (PW_OCC_BATCH),
+* k_rollout_occ (occupancy reject) with the push closure per thread and per warp (PW_OCC_WARP_CLOSURE=1),
 * the scan-every-step kernels it replaces (PW_NO_OCC=1),
 * the warp-per-environment layout of BASELINE.json's north star (PW_WARP_PER_ENV=1),
 each on the grouped and on the `e mod 223` interleaved batch, checked against each other.
@@ -43,7 +43,6 @@ def main():
     ap.add_argument("--steps", type=int, default=256)
     ap.add_argument("--envs", type=int, default=1 << 18)
     ap.add_argument("--out", default="")
-    ap.add_argument("--batches", type=int, nargs="*", default=[4, 8, 12, 16, 24])
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     keys = data.benchmark_keys()
@@ -58,12 +57,18 @@ def main():
     term = torch.empty((T, n), dtype=torch.uint8, device=dev)
     xy = eng.new_state(n)
     results = []
-    variants = [("occ batch=%d" % b, {"PW_OCC_BATCH": str(b)}) for b in args.batches]
-    variants += [("scan every step (round 1)", {"PW_NO_OCC": "1"}), ("warp per environment", {"PW_WARP_PER_ENV": "1"})]
+    variants = [("bounding-box mask prefilter, lock-step (k_rollout_mask)", {})]
+    variants += [("occupancy reject, run-ahead lanes, batched closure (k_rollout_occ_ra) batch=%d" % b,
+                  {"PW_OCC_MODE": "runahead", "PW_OCC_BATCH": str(b)}) for b in (8,)]
+    variants += [("occupancy reject, lock-step, per-thread closure (k_rollout_occ)", {"PW_OCC_MODE": "lockstep"}),
+                ("occupancy reject, lock-step, warp-per-environment closure",
+                 {"PW_OCC_MODE": "lockstep", "PW_OCC_WARP_CLOSURE": "1"}),
+                ("scan every step (round 1)", {"PW_NO_OCC": "1"}),
+                ("warp per environment for every step", {"PW_WARP_PER_ENV": "1"})]
     for layout, pid in layouts.items():
         ref = None
         for name, env in variants:
-            for k in ("PW_OCC_BATCH", "PW_NO_OCC", "PW_WARP_PER_ENV"):
+            for k in ("PW_OCC_WARP_CLOSURE", "PW_OCC_MODE", "PW_OCC_BATCH", "PW_NO_OCC", "PW_WARP_PER_ENV"):
                 os.environ.pop(k, None)
             os.environ.update(env)
 
@@ -81,7 +86,7 @@ def main():
                    "equal_to_first_variant": bool(same), "digest": digest}
             print(json.dumps(rec), flush=True)
             results.append(rec)
-    for k in ("PW_OCC_BATCH", "PW_NO_OCC", "PW_WARP_PER_ENV"):
+    for k in ("PW_OCC_WARP_CLOSURE", "PW_OCC_MODE", "PW_OCC_BATCH", "PW_NO_OCC", "PW_WARP_PER_ENV"):
         os.environ.pop(k, None)
     if args.out:
         os.makedirs(os.path.dirname(os.path.abspath(args.out)), exist_ok=True)

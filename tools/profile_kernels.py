@@ -32,7 +32,7 @@ if name == "step1":
 elif name == "mixed":
     keys = data.benchmark_keys()
     eng = Engine([data.puzzle_text(k) for k in keys], device=dev)
-    n, T = 1 << 18, 64
+    n, T = 1 << 18, 256
     ids = torch.sort(torch.arange(n) % len(keys), stable=True).values.to(torch.int32).to(dev)
     actions = torch.randint(0, 4, (T, n), dtype=torch.uint8, device=dev)
     reward = torch.empty((T, n), dtype=torch.float32, device=dev)
