@@ -127,17 +127,25 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------- CPU baseline
-def cpu_port_throughput(target_seconds: float, threads: int = 0):
-    """Times oracle/pw_oracle.c (the reference's table-driven algorithm restated in C, OpenMP
-    over environments) on a bounded sample of the SAME workload.  Returns (env-steps/s,
-    threads, sample description).  This is the one place bench.py executes oracle/."""
+def cpu_throughput(target_seconds: float, threads: int = 0, kind: str = "reference"):
+    """Times a CPU implementation of the SAME workload on a bounded sample: `kind` "reference" = the
+    reference's own C++ getNextState (cpp/src/pushworld_puzzle.cc compiled into oracle/_ref, every
+    OpenMP thread stepping its own copy of the puzzle), "port" = oracle/pw_oracle.c (the reference's
+    table-driven algorithm restated in C).  Falls back to "port" when oracle/_ref is not available.
+    Returns (env-steps/s, threads, sample description, kind).  bench.py executes oracle/ only here."""
     sys.path.insert(0, os.path.join(REPO, "oracle"))
     import numpy as np
 
     import c_oracle
+    import ref_oracle
     from pushworld_b200 import data
 
-    puzzle = c_oracle.COraclePuzzle(data.puzzle_text(PUZZLE_KEY))
+    text = data.puzzle_text(PUZZLE_KEY)
+    if kind == "reference" and ref_oracle.available():
+        puzzle = ref_oracle.RefPuzzle(text)
+    else:
+        kind = "port"
+        puzzle = c_oracle.COraclePuzzle(text)
     # all host threads this process may use (torchrun exports OMP_NUM_THREADS=1: ignore it)
     threads = threads or len(os.sched_getaffinity(0))
     rng = np.random.default_rng(ACTION_SEED)
@@ -158,7 +166,7 @@ def cpu_port_throughput(target_seconds: float, threads: int = 0):
     n_envs = max(1 << 12, int(rate * target_seconds / n_steps))
     n_envs = min(n_envs, 1 << 22)
     rate, done = run(n_envs, n_steps)
-    return rate, threads, f"{n_envs} envs x {n_steps} steps of {PUZZLE_KEY} ({done} env-steps)"
+    return rate, threads, f"{n_envs} envs x {n_steps} steps of {PUZZLE_KEY} ({done} env-steps)", kind
 
 
 def python_port_throughput(seconds: float = 3.0):
@@ -189,12 +197,12 @@ def run_reference(args) -> None:
         return
     # W warm-up + K timed steps; each step is a bounded sample of ~2 s of CPU work
     for _ in range(max(args.warmup, 1)):
-        cpu_port_throughput(0.3)
+        cpu_throughput(0.3)
     rates, t0 = [], time.perf_counter()
-    sample = ""
+    sample, kind = "", "reference"
     threads = 0
     for _ in range(args.steps):
-        rate, threads, sample = cpu_port_throughput(2.0)
+        rate, threads, sample, kind = cpu_throughput(2.0)
         rates.append(rate)
     elapsed = time.perf_counter() - t0
     value = statistics.mean(rates)
@@ -213,12 +221,15 @@ def run_reference(args) -> None:
         "dtype": "int32",
         "data": "synthetic",
         "config": _workload_config(args.gpus),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind,
                          "sample": sample + " per step"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "reference arm = oracle/pw_oracle.c (C port of the reference's table-driven "
-        "get_next_state; the Python reference cannot travel to the GPU box and its C++ twin "
-        "needs Boost), OpenMP over all host threads",
+        "note": "reference arm = the reference's own C++ getNextState + satisfiesGoal "
+        "(cpp/src/pushworld_puzzle.cc, compiled unmodified into oracle/_ref with a 5-function Boost "
+        "shim; the Python reference cannot travel to the GPU box), one copy of the puzzle per OpenMP "
+        "thread, all host threads" if kind == "reference" else
+        "reference arm = oracle/pw_oracle.c (C port of the reference's table-driven get_next_state): "
+        "oracle/_ref was not available",
     }
     print(json.dumps(line), file=_RESULT_OUT, flush=True)
 
@@ -541,7 +552,8 @@ def run_ours(args) -> None:
         # secondary bound: what limits the kernel when it is not HBM
         roofline["secondary_bound"] = traffic.get("secondary_bound")
 
-    cpu_rate, cpu_threads, cpu_sample = cpu_port_throughput(12.0)
+    cpu_rate, cpu_threads, cpu_sample, cpu_kind = cpu_throughput(12.0)
+    port_rate = cpu_throughput(4.0, kind="port")[0] if cpu_kind == "reference" else cpu_rate
     py_rate = python_port_throughput(3.0)
 
     line = {
@@ -559,8 +571,9 @@ def run_ours(args) -> None:
         "data": "synthetic",
         "config": _workload_config(world),
         "roofline": roofline,
-        "cpu_baseline": {"value": cpu_rate, "unit": UNIT, "cores": cpu_threads, "kind": "port",
+        "cpu_baseline": {"value": cpu_rate, "unit": UNIT, "cores": cpu_threads, "kind": cpu_kind,
                          "sample": cpu_sample,
+                         "c_port_all_cores": port_rate,
                          "python_port_single_core": py_rate},
         "e2e": {
             "value": e2e_value,

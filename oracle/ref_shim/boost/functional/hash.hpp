@@ -5,8 +5,14 @@
 // two entry points it calls, with Boost's published combining formula.
 #ifndef PW_REF_SHIM_BOOST_FUNCTIONAL_HASH_HPP_
 #define PW_REF_SHIM_BOOST_FUNCTIONAL_HASH_HPP_
+// (the real Boost headers pull in these standard headers, which the reference then relies on)
+#include <algorithm>
+#include <climits>
 #include <cstddef>
+#include <fstream>
 #include <functional>
+#include <stdexcept>
+#include <string>
 
 namespace boost {
 

@@ -86,39 +86,7 @@ def test_visited_insert_is_exact(golden):
     assert engine.poll_status()[1] > 0
 
 
-class _NoveltyModel:
-    """cpp/src/heuristics/novelty.cc:30-77 restated with python sets."""
-
-    def __init__(self, n):
-        self.singles = [set() for _ in range(n)]
-        self.pairs = {}
-        self.n = n
-
-    def evaluate(self, state, moved_idx, insert=True):
-        novelty = 3
-        new_singles, new_pairs = [], []
-        for i in moved_idx:
-            if state[i] not in self.singles[i]:
-                novelty = 1
-                new_singles.append((i, state[i]))
-            for j in range(self.n):
-                if j == i:
-                    continue
-                a, b = (i, j) if i < j else (j, i)
-                key = (a, b, state[a], state[b])
-                if key not in self.pairs:
-                    if novelty > 2:
-                        novelty = 2
-                    new_pairs.append(key)
-        if insert:
-            self.insert(new_singles, new_pairs)
-        return novelty, new_singles, new_pairs
-
-    def insert(self, singles, pairs):
-        for i, p in singles:
-            self.singles[i].add(p)
-        for key in pairs:
-            self.pairs[key] = True
+from tests.test_ref_oracle import NoveltyModel as _NoveltyModel  # noqa: E402  (pinned against oracle/_ref there)
 
 
 def test_novelty_sequential_and_batched(golden):
@@ -143,10 +111,16 @@ def test_novelty_sequential_and_batched(golden):
     # sequential: one state per call
     seen = engine.novelty_table(0)
     model = _NoveltyModel(oracle.num_objects)
+    import ref_oracle
+
+    # the reference's own NoveltyHeuristic (cpp/src/heuristics/novelty.cc, built into oracle/_ref)
+    ref_h = ref_oracle.RefNovelty(oracle.num_objects) if ref_oracle.available() else None
     for t in range(400):
         got = int(engine.novelty(arena, 0, t, 1, moved[t:t + 1], seen).item())
         want, _, _ = model.evaluate(*stream[t])
         assert got == want, t
+        if ref_h is not None:
+            assert got == ref_h.evaluate(stream[t][0], sum(1 << k for k in stream[t][1])), t
 
     # batched: whole batches judged against the table before the call
     seen = engine.novelty_table(0)
