@@ -33,7 +33,7 @@ PUZZLE_KEY = "level1/Road Block"
 N_ENVS = 1 << 18
 T_STEPS = 1024
 ACTION_SEED = 1234
-ROLLOUT_KERNEL = "k_rollout_ring<3, true> (pw_rollout)"
+ROLLOUT_KERNEL = "k_rollout_table<plain, compact> (pw_rollout on the reachable-state transition table)"
 
 
 def _workload_config(n_gpus: int) -> dict:

@@ -25,7 +25,7 @@ NVCC_FLAGS = [
 # one object per translation unit, compiled in parallel and linked into one shared library; no
 # relocatable device code: every kernel file is self-contained (device tables that several files
 # need are uploaded once per file)
-SOURCES = ["pw_kernels.cu", "pw_occ.cu", "pw_render.cu", "pw_abi.cu", "pw_compile.cpp"]
+SOURCES = ["pw_kernels.cu", "pw_occ.cu", "pw_table.cu", "pw_render.cu", "pw_abi.cu", "pw_compile.cpp"]
 
 
 def _nvcc() -> str:

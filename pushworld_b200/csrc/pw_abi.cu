@@ -5,6 +5,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -65,6 +66,7 @@ struct PwEngine {
   uint32_t* d_off = nullptr;
   unsigned long long* d_status = nullptr;  // [4]
   pw::BoardStaticPod* d_board_static = nullptr;  // [num_puzzles]
+  std::vector<pw::StateTableView> state_tables;   // per puzzle; n_states = 0: not tabulated
   std::vector<int> board_bits;                    // per puzzle, 1 << 30 = not eligible
   int board_bits_all = 1 << 30;                   // max over all puzzles (mixed board kernel)
 };
@@ -275,6 +277,7 @@ int pw_engine_create(const void* blob, size_t blob_bytes, const uint32_t* offset
     for (int dg = -kMaxObjects; dg <= kMaxObjects; ++dg)
       lut[dg + kMaxObjects] = (float)((double)dg - 0.01);
     err = upload_reward_lut(lut);
+    if (err == cudaSuccess) err = upload_reward_lut_table(lut);
   }
   if (err == cudaSuccess) {
     // puzzle.py:65-79; index 0 = background 255, 12 = zero padding (env_utils.py:84-91)
@@ -295,6 +298,38 @@ int pw_engine_create(const void* blob, size_t blob_bytes, const uint32_t* offset
     err = configure_kernels((size_t)1 << 30);
   }
   if (err == cudaSuccess) err = configure_occ_kernels();
+  if (err == cudaSuccess) err = configure_table_kernels();
+  // Reachable-state transition tables (pw_table.cu) for engines over a few small puzzles -- the
+  // single-puzzle engines of the drop-in environments and of BASELINE config 2.  Enumerated on the
+  // device with the exact rule; a puzzle with more states than a CTA can stage is simply not tabulated.
+  e->state_tables.assign((size_t)num_puzzles, StateTableView{});
+  if (err == cudaSuccess && num_puzzles <= 4 && getenv("PW_NO_TABLE") == nullptr) {
+    const int max_states = state_table_max_states();
+    for (int p = 0; p < num_puzzles && err == cudaSuccess; ++p) {
+      const PuzzleInfo& info = e->puzzles[(size_t)p];
+      int bits = 1;
+      while ((1 << bits) < info.width * info.height) ++bits;
+      if (info.n * bits > 63 || info.width * info.height > 4096) continue;
+      StateTableView tv{};
+      tv.key_bits = bits;
+      tv.goals = info.g;
+      tv.hash_cap = 1 << 16;  // >= 4 x the largest table
+      if (err == cudaSuccess) err = cudaMalloc(&tv.keys, sizeof(uint64_t) * (size_t)max_states);
+      if (err == cudaSuccess) err = cudaMalloc(&tv.table, sizeof(uint32_t) * 4 * (size_t)max_states);
+      if (err == cudaSuccess) err = cudaMalloc(&tv.hash_keys, sizeof(unsigned long long) * (size_t)tv.hash_cap);
+      if (err == cudaSuccess) err = cudaMalloc(&tv.hash_vals, sizeof(uint32_t) * (size_t)tv.hash_cap);
+      if (err == cudaSuccess) err = cudaMemset(tv.hash_keys, 0, sizeof(unsigned long long) * (size_t)tv.hash_cap);
+      if (err == cudaSuccess) tv.n_states = build_state_table(e->d_blob, packed_off[(size_t)p], tv, max_states, &err);
+      if (err != cudaSuccess || tv.n_states == 0) {
+        cudaFree(tv.keys);
+        cudaFree(tv.table);
+        cudaFree(tv.hash_keys);
+        cudaFree(tv.hash_vals);
+        tv = StateTableView{};
+      }
+      e->state_tables[(size_t)p] = tv;
+    }
+  }
   if (err == cudaSuccess) err = configure_render_kernels();
   if (err != cudaSuccess) {
     const int rc = cuda_error(err, "pw_engine_create");
@@ -312,6 +347,12 @@ int pw_engine_destroy(PwEngine* e) {
   if (e->d_off) cudaFree(e->d_off);
   if (e->d_status) cudaFree(e->d_status);
   if (e->d_board_static) cudaFree(e->d_board_static);
+  for (const StateTableView& tv : e->state_tables) {
+    if (tv.keys) cudaFree(tv.keys);
+    if (tv.table) cudaFree(tv.table);
+    if (tv.hash_keys) cudaFree(tv.hash_keys);
+    if (tv.hash_vals) cudaFree(tv.hash_vals);
+  }
   delete e;
   return PW_OK;
 }
@@ -402,6 +443,7 @@ int pw_rollout(PwEngine* e, int64_t n_envs, int32_t n_steps, const int32_t* puzz
     if (p.board_bits <= 32 && ring_fits(p.board_bits, info.width - 1)) p.ring_goals = info.g;
   }
   p.board_static = puzzle_id ? e->d_board_static : e->d_board_static + puzzle_uniform;
+  if (!puzzle_id) p.state_table = e->state_tables[(size_t)puzzle_uniform];
   p.x = x;
   p.y = y;
   p.stride = stride;
@@ -498,6 +540,7 @@ int pw_rollout_packed(PwEngine* e, int64_t n_envs, int32_t n_steps, int32_t* puz
     if (p.board_bits <= 32 && ring_fits(p.board_bits, info.width - 1)) p.ring_goals = info.g;
   }
   p.board_static = puzzle_id ? e->d_board_static : e->d_board_static + puzzle_uniform;
+  if (!puzzle_id) p.state_table = e->state_tables[(size_t)puzzle_uniform];
   p.x = x;
   p.y = y;
   p.stride = stride;

@@ -18,6 +18,18 @@ struct BoardStaticPod {
   int32_t P, n, g, bits;  // bits = 1 << 30 when the puzzle is not eligible
 };
 
+// Reachable-state transition table of one puzzle (pw_table.cu), device arrays owned by the engine.
+struct StateTableView {
+  uint64_t* keys;                 // [n_states] packed state of every index
+  uint32_t* table;                // [n_states * 4] successor | record << 16 | moved << 24 | gained << 25
+  unsigned long long* hash_keys;  // [hash_cap] open addressing, key + 1 (0 = empty)
+  uint32_t* hash_vals;            // [hash_cap] index of the key
+  int32_t n_states;               // 0 = the puzzle is not tabulated
+  int32_t hash_cap;               // power of two
+  int32_t key_bits;               // bits per object in a packed state (cell index y * W + x)
+  int32_t goals;                  // the puzzle's number of goal objects
+};
+
 struct StepParams {
   const uint64_t* blob;        // all puzzle tables, device
   const uint32_t* puzzle_off;  // u64 offset of each puzzle inside blob, device
@@ -34,6 +46,7 @@ struct StepParams {
   int32_t occ_warp_closure;  // set by launch_rollout_occ (pw_occ.cu): closure per warp instead of per thread
   int32_t episode_tiles;  // set by launch_steps: pw_rollout_episodes with reward + terminated (+ truncated), whole warps
   const BoardStaticPod* board_static;  // device; entry of puzzle_uniform (valid if board_bits <= 64)
+  StateTableView state_table;          // of puzzle_uniform (n_states = 0: none)
   int32_t* x;
   int32_t* y;
   int64_t stride;
@@ -149,6 +162,7 @@ struct RenderParams {
 };
 
 cudaError_t upload_reward_lut(const float* host_lut);
+cudaError_t upload_reward_lut_table(const float* host_lut);  // pw_table.cu's copy
 cudaError_t configure_kernels(size_t max_dynamic_smem);
 cudaError_t configure_render_kernels();
 // n_limit: max objects over the puzzles this launch can touch (selects the register policy)
@@ -157,6 +171,13 @@ cudaError_t launch_steps(const StepParams& p, int n_limit, cudaStream_t stream);
 bool occ_rollout_eligible(const StepParams& p);
 cudaError_t launch_rollout_occ(const StepParams& p, cudaStream_t stream);
 cudaError_t configure_occ_kernels();
+// pw_table.cu: rollouts of a small puzzle on its reachable-state transition table
+int state_table_max_states();
+int build_state_table(const uint64_t* d_blob, uint32_t puzzle_off, const StateTableView& tv, int max_states,
+                      cudaError_t* err);
+bool table_rollout_eligible(const StepParams& p);
+cudaError_t launch_rollout_table(const StepParams& p, cudaStream_t stream);
+cudaError_t configure_table_kernels();
 cudaError_t launch_expand(const ExpandParams& p, int n_limit, cudaStream_t stream);
 cudaError_t launch_reset(const ResetParams& p, cudaStream_t stream);
 cudaError_t launch_goals(const GoalParams& p, cudaStream_t stream);

@@ -1025,6 +1025,8 @@ cudaError_t launch_steps(const StepParams& p_in, int n_limit, cudaStream_t strea
   p.episode_tiles = whole_warps && p.flags == (kFlagAutoreset | kFlagResample) && (plain_out || packed_out) &&
                     !p.dgoals && !p.moved && !p.return_sum && p.steps && p.puzzle_id_mut && p.episode &&
                     (int64_t)p.T * p.N < ((int64_t)1 << 32);
+  // a small puzzle with a reachable-state transition table: the rollout is table look-ups (pw_table.cu)
+  if (table_rollout_eligible(p)) return launch_rollout_table(p, stream);
   const unsigned grid = grid_for(p.N);
   const size_t state_bytes = (size_t)p.n_max * 2 * kBlock * sizeof(int);
   const bool lean = is_lean(p);
