@@ -367,6 +367,71 @@ def run_configs(rank, world, dev, peak, sampler, reps=5):
     return out
 
 
+def run_latency(dev):
+    """Per-call latency of the per-step surfaces (rank 0, 1 GPU): the N=1 gym drop-in's step()
+    (action in, step + render, observation + reward + flags + state back on the host) beside the
+    CPU port of the reference's PushWorldEnv.step, and one vector-environment step of 2^18
+    environments replayed as a CUDA graph."""
+    import random
+
+    import torch
+
+    sys.path.insert(0, os.path.join(REPO, "oracle"))
+    import pushworld_oracle as po
+    from pushworld_b200 import data
+    from pushworld_b200.gym_env import PushWorldEnv
+    from pushworld_b200.vector_env import PushWorldVectorEnv
+
+    root = data.materialize()
+    path = os.path.join(root, PUZZLE_KEY + ".pwp")
+    env = PushWorldEnv(path)
+    env.reset()
+    rng = random.Random(7)
+    for _ in range(20):
+        env.step(rng.randrange(4))
+    n_steps = 300
+    t0 = time.perf_counter()
+    for _ in range(n_steps):
+        env.step(rng.randrange(4))
+    dropin_us = (time.perf_counter() - t0) / n_steps * 1e6
+    # the reference's step() restated on the CPU (oracle/pushworld_oracle.py: OracleEnv), same puzzle
+    cpu_env = po.OracleEnv([po.OraclePuzzle(data.puzzle_text(PUZZLE_KEY))])
+    cpu_env.reset()
+    t0 = time.perf_counter()
+    n_cpu = 0
+    while time.perf_counter() - t0 < 2.0:
+        cpu_env.step(rng.randrange(4))
+        n_cpu += 1
+    cpu_us = (time.perf_counter() - t0) / n_cpu * 1e6
+    # vector step, 2^18 environments, no observation: one CUDA-graph replay per step
+    venv = PushWorldVectorEnv([data.puzzle_text(PUZZLE_KEY)], N_ENVS, puzzle_ids=0, device=dev)
+    venv.reset()
+    step = venv.capture_step()
+    step.actions.copy_(torch.randint(0, 4, (N_ENVS,), dtype=torch.uint8, device=dev))
+    for _ in range(20):
+        step.replay()
+    torch.cuda.synchronize()
+    n_rep = 500
+    t0 = time.perf_counter()
+    for _ in range(n_rep):
+        step.replay()
+    torch.cuda.synchronize()
+    vec_us = (time.perf_counter() - t0) / n_rep * 1e6
+    return {
+        "dropin_gym_step_us": dropin_us,
+        "dropin_gym_steps_per_s": 1e6 / dropin_us,
+        "cpu_port_gym_step_us": cpu_us,
+        "cpu_port_gym_steps_per_s": 1e6 / cpu_us,
+        "dropin_vs_cpu_port": cpu_us / dropin_us,
+        "vector_step_graph_replay_us": vec_us,
+        "vector_step_env_steps_per_s": N_ENVS / (vec_us * 1e-6),
+        "note": "N=1 drop-in: pushworld_b200.gym_env.PushWorldEnv.step on level1/Road Block, observation "
+        "(100,160,3) float32 + reward + flags + state read back through pinned buffers, one CUDA-graph "
+        "replay + one stream synchronisation per call; vector step: PushWorldVectorEnv.capture_step().replay() "
+        "for 2^18 environments (wall clock per call incl. the launch, device-synchronised at the end)",
+    }
+
+
 def run_ours(args) -> None:
     import torch
 
@@ -513,6 +578,8 @@ def run_ours(args) -> None:
 
     peak, peak_src = _peak()
     configs = run_configs(rank, world, dev, peak, sampler) if not args.no_configs else {}
+    latency = run_latency(dev) if (rank == 0 and not args.no_configs) else None
+    distributed.barrier()
     clocks = sampler.stop() if rank == 0 else None
     if rank != 0:
         return
@@ -605,6 +672,7 @@ def run_ours(args) -> None:
             "count come back; per-step arrays stay on the device)",
         },
         "configs": configs,
+        "per_step_latency": latency,
         "gpu_launches": 2 * args.steps,
         "gpu_launches_e2e": (1 + chunks) * e2e_steps,
         "clocks": clocks,

@@ -57,12 +57,36 @@ class SingleEnvCore:
         self.current_state: Optional[State] = None
         self.steps = 0
         dev = self.engine.device
-        self._xy = self.engine.new_state(1)
-        self._pid = torch.zeros(1, dtype=torch.int32, device=dev)
-        self._action = torch.zeros(1, dtype=torch.uint8, device=dev)
-        self._steps_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        n_max = self.engine.n_max
         self.observation_shape = (self.max_cell_height * pixels_per_cell,
                                   self.max_cell_width * pixels_per_cell, 3)
+        # Everything a step returns besides the observation lives in ONE small device buffer --
+        # state (int32 [2, n_max, 1]) | reward f32 | steps i32 | dgoals i8 | terminated u8 | truncated u8 --
+        # so that a step reads it back with one copy into pinned host memory; the observation is
+        # rendered into a second buffer with its own pinned twin.  One stream synchronisation per step.
+        state_bytes = 8 * n_max
+        self._meta_dev = torch.zeros(state_bytes + 12, dtype=torch.uint8, device=dev)
+        self._meta_host = torch.zeros(state_bytes + 12, dtype=torch.uint8).pin_memory()
+        self._xy = self._meta_dev[:state_bytes].view(torch.int32).view(2, n_max, 1)
+        self._steps_dev = self._meta_dev[state_bytes + 4:state_bytes + 8].view(torch.int32)
+        from .engine import StepOutput
+
+        self._out = StepOutput(
+            reward=self._meta_dev[state_bytes:state_bytes + 4].view(torch.float32),
+            dgoals=self._meta_dev[state_bytes + 8:state_bytes + 9].view(torch.int8),
+            terminated=self._meta_dev[state_bytes + 9:state_bytes + 10],
+            truncated=self._meta_dev[state_bytes + 10:state_bytes + 11],
+        )
+        self._state_bytes = state_bytes
+        self._meta_np = self._meta_host.numpy()
+        self._obs_dev = torch.empty((1,) + self.observation_shape, dtype=torch.float32, device=dev)
+        self._obs_host = torch.empty(self.observation_shape, dtype=torch.float32).pin_memory()
+        self._pid = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._action = torch.zeros(1, dtype=torch.uint8, device=dev)
+        self._action_host = torch.zeros(1, dtype=torch.uint8).pin_memory()
+        self._graph = None       # CUDA graph of one step: action in, step + render, both read-backs
+        self._graph_failed = False
+        self._stream = torch.cuda.Stream(dev)
 
     @property
     def current_puzzle(self) -> Optional[PushWorldPuzzle]:
@@ -72,39 +96,82 @@ class SingleEnvCore:
         return (self.max_cell_height, self.max_cell_width)
 
     def _state_tuple(self) -> State:
+        """The current state from the pinned copy of the meta buffer (no device access)."""
         n = self.puzzles[self.current_index].num_movables
-        host = self._xy.cpu().numpy()
-        return tuple((int(host[0, j, 0]), int(host[1, j, 0])) for j in range(n))
+        n_max = self.engine.n_max
+        xy = self._meta_np[:self._state_bytes].view(np.int32)
+        return tuple((int(xy[j]), int(xy[n_max + j])) for j in range(n))
 
     def reset(self, seed: Optional[int] = None) -> np.ndarray:
         if seed is not None:
             self.rng = random.Random(seed)
         self.current_index = self.rng.choice(range(len(self.puzzles)))  # gym_env.py:174
-        self._pid.fill_(self.current_index)
-        self.engine.reset(self._xy, self._pid, steps=self._steps_dev)
+        with torch.cuda.stream(self._stream):
+            self._pid.fill_(self.current_index)
+            self.engine.reset(self._xy, self._pid, steps=self._steps_dev)
+            self.engine.render(self._xy, self._pid, dtype="float32", pixels_per_cell=self.pixels_per_cell,
+                               border_width=self.border_width, pad_cells=self._pad(), out=self._obs_dev)
+            self._meta_host.copy_(self._meta_dev, non_blocking=True)
+            self._obs_host.copy_(self._obs_dev[0], non_blocking=True)
+        self._stream.synchronize()
         self.steps = 0
         self.current_state = self._state_tuple()
-        obs = self.engine.render(self._xy, self._pid, dtype="float32",
-                                 pixels_per_cell=self.pixels_per_cell,
-                                 border_width=self.border_width, pad_cells=self._pad())
-        return obs[0].cpu().numpy()
+        return self._obs_host.numpy().copy()
+
+    def _enqueue_step(self) -> None:
+        """Action in, step + render (pw_step_render), both read-backs: all asynchronous."""
+        self._action.copy_(self._action_host, non_blocking=True)
+        self.engine.step_render(
+            self._xy, self._pid, self._action, dtype="float32",
+            pixels_per_cell=self.pixels_per_cell, border_width=self.border_width,
+            pad_cells=self._pad(), steps=self._steps_dev, max_steps=self.max_steps,
+            out=self._obs_dev, step_out=self._out)
+        self._meta_host.copy_(self._meta_dev, non_blocking=True)
+        self._obs_host.copy_(self._obs_dev[0], non_blocking=True)
+
+    def _capture(self) -> None:
+        """Captures one step as a CUDA graph (replayed by every later step: one launch call)."""
+        try:
+            with torch.cuda.stream(self._stream):
+                self._enqueue_step()  # warm-up outside the capture (lazy initialisation, allocator)
+            self._stream.synchronize()
+            # the warm-up advanced the environment: put the state and the step counter back
+            self._meta_dev.copy_(self._saved_meta)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=self._stream):
+                self._enqueue_step()
+            self._stream.synchronize()
+            self._meta_dev.copy_(self._saved_meta)
+            torch.cuda.current_stream(self.engine.device).synchronize()
+            self._graph = graph
+        except Exception:  # capture not possible here: keep launching the same work directly (still on the GPU)
+            self._graph_failed = True
+            self._meta_dev.copy_(self._saved_meta)
+            torch.cuda.current_stream(self.engine.device).synchronize()
 
     def step(self, action: int):
         """-> (observation, reward (python float), terminated, truncated)"""
         if self.current_state is None:
             raise RuntimeError("reset() must be called before step() can be called.")
         self.steps += 1
-        self._action.fill_(int(action))
-        obs, out = self.engine.step_render(
-            self._xy, self._pid, self._action, dtype="float32",
-            pixels_per_cell=self.pixels_per_cell, border_width=self.border_width,
-            pad_cells=self._pad(), steps=self._steps_dev, max_steps=self.max_steps)
-        terminated = bool(out.terminated.item())
+        self._action_host[0] = int(action)
+        if self._graph is None and not self._graph_failed:
+            self._saved_meta = self._meta_dev.clone()
+            torch.cuda.current_stream(self.engine.device).synchronize()
+            self._capture()
+        with torch.cuda.stream(self._stream):
+            if self._graph is not None:
+                self._graph.replay()
+            else:
+                self._enqueue_step()
+        self._stream.synchronize()
+        sb = self._state_bytes
+        terminated = bool(self._meta_np[sb + 9])
         # gym_env.py:212-221 in python floats, from the kernel's exact integer goal delta
-        reward = 10.0 if terminated else int(out.dgoals.item()) - 0.01
-        truncated = bool(out.truncated.item())
+        reward = 10.0 if terminated else int(self._meta_np[sb + 8:sb + 9].view(np.int8)[0]) - 0.01
+        truncated = bool(self._meta_np[sb + 10])
         self.current_state = self._state_tuple()
-        return obs[0].cpu().numpy(), reward, terminated, truncated
+        return self._obs_host.numpy().copy(), reward, terminated, truncated
 
     def render_uint8(self) -> np.ndarray:
         return self.puzzles[self.current_index].render(

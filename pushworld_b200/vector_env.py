@@ -229,6 +229,14 @@ class PushWorldVectorEnv:
             raise ValueError("The provided action is not in the action space.")  # gym_env.py:195
         return obs, out.reward, out.terminated, out.truncated, {"dgoals": out.dgoals}
 
+    def capture_step(self) -> "GraphedStep":
+        """One ``step`` (plus the observation render, if enabled) captured as a CUDA graph: the
+        returned object owns a static ``actions`` tensor (uint8 [N]; write the policy's actions into
+        it in place) and static output tensors; ``replay()`` enqueues the whole step with ONE launch
+        call.  Invalid actions are counted, not raised (poll ``engine.poll_invalid_actions()``)."""
+        self._require_reset()
+        return GraphedStep(self)
+
     def _as_actions(self, actions, shape) -> torch.Tensor:
         if not isinstance(actions, torch.Tensor):
             actions = torch.as_tensor(np.asarray(actions))
@@ -356,6 +364,54 @@ class PushWorldVectorEnv:
             pipe = _HostPipe(self.device, self.num_envs, chunk_steps)
             self._pipe = pipe
         return pipe
+
+
+class GraphedStep:
+    """A vector-environment step as a replayable CUDA graph (see ``PushWorldVectorEnv.capture_step``)."""
+
+    def __init__(self, env: "PushWorldVectorEnv") -> None:
+        dev, n = env.device, env.num_envs
+        self.env = env
+        self.actions = torch.zeros(n, dtype=torch.uint8, device=dev)
+        self.out = StepOutput(
+            reward=torch.empty(n, dtype=torch.float32, device=dev),
+            dgoals=torch.empty(n, dtype=torch.int8, device=dev),
+            terminated=torch.empty(n, dtype=torch.uint8, device=dev),
+            truncated=torch.empty(n, dtype=torch.uint8, device=dev),
+        )
+        self.observation = None
+        if env.observation is not None:
+            tdtype = torch.float32 if env.observation == "float32" else torch.uint8
+            self.observation = torch.empty((n,) + env.observation_shape, dtype=tdtype, device=dev)
+        self._stream = torch.cuda.Stream(dev)
+        saved = (env.xy.clone(), env.steps.clone())
+        self._stream.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(self._stream):
+            self._enqueue()  # warm-up outside the capture
+        self._stream.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph, stream=self._stream):
+            self._enqueue()
+        self._stream.synchronize()
+        env.xy.copy_(saved[0])  # the warm-up stepped the environments: put them back
+        env.steps.copy_(saved[1])
+        torch.cuda.current_stream(dev).synchronize()
+
+    def _enqueue(self) -> None:
+        env = self.env
+        if self.observation is None:
+            env.engine.step(env.xy, env._sel, self.actions, steps=env.steps, max_steps=env.max_steps, out=self.out)
+        else:
+            env.engine.step_render(env.xy, env._sel, self.actions, dtype=env.observation,
+                                   pixels_per_cell=env.pixels_per_cell, border_width=env.border_width,
+                                   pad_cells=env.pad_cells, steps=env.steps, max_steps=env.max_steps,
+                                   out=self.observation, step_out=self.out)
+
+    def replay(self):
+        """-> (observation or None, reward, terminated, truncated): static tensors, overwritten by
+        the next replay.  Runs on the current stream."""
+        self.graph.replay()
+        return self.observation, self.out.reward, self.out.terminated, self.out.truncated
 
 
 class _HostPipe:

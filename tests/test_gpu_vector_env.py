@@ -176,3 +176,33 @@ def test_prepared_step_equals_step(golden):
             first = r_b
         assert r_b is first  # the same tensor every step
     assert torch.equal(a.xy, b.xy) and torch.equal(a.steps, b.steps)
+
+
+def test_graphed_step_equals_plain_steps():
+    """PushWorldVectorEnv.capture_step(): a step replayed as a CUDA graph gives the same rewards,
+    flags, observations and states as step() (gym_env.py:188-226 semantics, incl. max_steps)."""
+    import torch
+
+    from pushworld_b200 import data
+    from pushworld_b200.vector_env import PushWorldVectorEnv
+
+    texts = [data.puzzle_text(k) for k in ("level1/Road Block", "level1/Many Small Tools", "level2/Pull Dont Push")]
+    n = 96
+    for observation in (None, "uint8"):
+        a = PushWorldVectorEnv(texts, n, max_steps=7, observation=observation)
+        b = PushWorldVectorEnv(texts, n, max_steps=7, observation=observation)
+        a.reset()
+        b.reset()
+        step = b.capture_step()
+        gen = torch.Generator(device="cuda").manual_seed(3)
+        for t in range(12):
+            actions = torch.randint(0, 4, (n,), dtype=torch.uint8, device="cuda", generator=gen)
+            obs_a, rew_a, term_a, trunc_a, _ = a.step(actions)
+            step.actions.copy_(actions)
+            obs_b, rew_b, term_b, trunc_b = step.replay()
+            torch.cuda.synchronize()
+            assert torch.equal(rew_a, rew_b) and torch.equal(term_a, term_b) and torch.equal(trunc_a, trunc_b), t
+            assert torch.equal(a.xy, b.xy) and torch.equal(a.steps, b.steps)
+            if observation is not None:
+                assert torch.equal(obs_a, obs_b)
+        assert bool(trunc_a.any())
