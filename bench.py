@@ -321,6 +321,38 @@ def run_configs(rank, world, dev, peak, sampler, reps=5):
         del env, actions, ro
     torch.cuda.empty_cache()
 
+    # ---- the reference's real level-0 set (15,400 generated puzzles), RL-style episodes ------
+    l0_keys = data.level0_keys()
+    eng = Engine([data.level0_text(k) for k in l0_keys], device=dev)
+    lo, hi = distributed.shard_range(1 << 18, rank, world)
+    n, T0 = hi - lo, 256
+    gen = torch.Generator(device=dev).manual_seed(4321 + rank)
+    pid = torch.randint(0, len(l0_keys), (n,), dtype=torch.int32, device=dev, generator=gen)
+    actions = torch.randint(0, 4, (T0, n), dtype=torch.uint8, device=dev, generator=gen)
+    xy = eng.new_state(n)
+    steps = torch.zeros(n, dtype=torch.int32, device=dev)
+    episode = torch.zeros(n, dtype=torch.int32, device=dev)
+    reward = torch.empty((T0, n), dtype=torch.float32, device=dev)
+    term = torch.empty((T0, n), dtype=torch.uint8, device=dev)
+    trunc = torch.empty((T0, n), dtype=torch.uint8, device=dev)
+    eng.reset(xy, pid, steps=steps)
+
+    def run_level0():
+        eng.rollout_episodes(xy, pid, actions, steps, episode, seed=11, max_steps=100,
+                             reward=reward, terminated=term, truncated=trunc)
+
+    sampler.mark_begin()
+    ms = _timed(run_level0, reps, 2, dev, distributed)
+    sampler.mark_end()
+    record("level0_real_episodes",
+           "all 15,400 puzzles of the reference's benchmark/puzzles/level0.zip in ONE engine, 2^18 envs with "
+           "random puzzle ids, pw_rollout_episodes (max_steps=100, puzzle re-sampled on the device after "
+           "every episode), T=256, reward f32 + terminated u8 + truncated u8 per step",
+           "k_rollout_mask<plain, episodes>", (1 << 18) * T0, ms, 7.0 + 16.0 * 4 / T0, 16.0 * 4 + 7.0,
+           {"unit": "env-steps", "episodes_finished": int(episode.sum().item())})
+    del eng, xy, pid, actions, reward, term, trunc, steps, episode
+    torch.cuda.empty_cache()
+
     # ---- config 4: successor expansion of a 10M-state frontier ------------------------------
     eng = Engine([data.puzzle_text("level2/Pull Dont Push")], device=dev)
     lo, hi = distributed.shard_range(10_000_000, rank, world)

@@ -169,6 +169,7 @@ cudaError_t configure_render_kernels();
 cudaError_t launch_steps(const StepParams& p, int n_limit, cudaStream_t stream);
 // pw_occ.cu: plain / packed rollouts of the general rule (occupancy reject + batched closure)
 bool occ_rollout_eligible(const StepParams& p);
+bool occ_episodes_eligible(const StepParams& p);
 cudaError_t launch_rollout_occ(const StepParams& p, cudaStream_t stream);
 cudaError_t configure_occ_kernels();
 // pw_table.cu: rollouts of a small puzzle on its reachable-state transition table

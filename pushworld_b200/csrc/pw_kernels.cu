@@ -1050,6 +1050,14 @@ cudaError_t launch_steps(const StepParams& p_in, int n_limit, cudaStream_t strea
 #undef PW_BOARD_MIXED
     return cudaGetLastError();
   }
+  // episode handling (autoreset / re-sampling) on the general rule: the mask kernel of pw_occ.cu
+  // (a single board-eligible puzzle keeps its bitboard kernel)
+  {
+    const bool board_uniform = p.puzzle_id == nullptr && p.board_bits <= 64 && n_limit <= 8 &&
+                               (size_t)p.uniform_u64 * 8 <= kStageLimit;
+    if (getenv("PW_NO_OCC") == nullptr && !board_uniform && occ_episodes_eligible(p))
+      return launch_rollout_occ(p, stream);
+  }
   if (p.flags & kFlagResample) {  // puzzles change mid-rollout: dynamic-n policy, global tables
     k_steps_mixed<0, false><<<grid, kBlock, state_bytes, stream>>>(p);
     return cudaGetLastError();

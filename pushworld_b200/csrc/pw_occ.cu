@@ -855,6 +855,16 @@ struct MaskEnv : EnvBase<GlobalTable> {
       y[j * stride + e] = this->y(j);
     }
   }
+  __device__ __forceinline__ void load_initial() {  // plain layout
+    masks = false;
+    const uint32_t v0 = this->table_desc(0, 1);
+    ax = lo16(v0);
+    ay = hi16(v0);
+    for (int j = 1; j < this->n_; ++j) {
+      const uint32_t v = this->table_desc(j, 1);
+      sm[(j - 1) * kOccBlock] = make_uint2((uint32_t)lo16(v), (uint32_t)hi16(v));
+    }
+  }
   __device__ __forceinline__ uint32_t desc(int j) const { return this->table_desc(j, 0); }
   __device__ __forceinline__ uint32_t desc_dyn(int j) const { return this->table_desc(j, 0); }
   // plain layout: (x, y); mask layout: (row mask, column mask)
@@ -891,7 +901,10 @@ struct MaskEnv : EnvBase<GlobalTable> {
 
 __device__ __forceinline__ uint32_t shift_mask(uint32_t m, int d) { return d > 0 ? m << 1 : (d < 0 ? m >> 1 : m); }
 
-template <bool kPacked>
+// kEpisodes: step counter, truncation (gym_env.py:223) and -- after a terminated or truncated step -- a
+// restart from the initial state, of a freshly drawn puzzle under pw_rollout_episodes' flag
+// (gym_env.py:171-176 on the device); the per-puzzle constants below are then derived again.
+template <bool kPacked, bool kEpisodes>
 __global__ void __launch_bounds__(kOccBlock)
     k_rollout_mask(const __grid_constant__ StepParams p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -915,48 +928,63 @@ __global__ void __launch_bounds__(kOccBlock)
   const int64_t e = (int64_t)blockIdx.x * kOccBlock + tid;
   StepCounts c;
   if (e < p.N) {  // whole warps (the launcher requires N % 32 == 0)
-    const int pid = p.puzzle_id ? p.puzzle_id[e] : p.puzzle_uniform;
+    int pid = p.puzzle_id ? p.puzzle_id[e] : p.puzzle_uniform;
     MaskEnv env;
     env.init(GlobalTable{p.blob + p.puzzle_off[pid]}, s_obj + tid);
     env.load(p.x, p.y, p.stride, e);
-    const int n = env.n(), g = env.g(), W = env.width(), H = env.height();
-    const uint32_t nn1 = 1u + (uint32_t)(n * n);
-    // the agent's wall table (pw_fast.cuh: tab_wall), descriptor cached in registers
-    const uint64_t wd = env.fast(nn1);
-    const uint32_t aw_hi = (uint32_t)(wd >> 32);
-    const uint32_t aw_xmax = aw_hi & 63u, aw_ymax = (aw_hi >> 6) & 0xfffu, aw_w = aw_hi >> 18;
-    const uint32_t aw_word0 = (uint32_t)wd << 1;
-    const uint32_t d0 = env.desc(0);
-    const int w0 = desc_w(d0), h0 = desc_h(d0);
-    // mask layout: grid of at most 32 x 32 cells, every movable inside it and off the walls (such a
-    // movable is stopped by the border walls, puzzle.py:160-168, 284-293, so it stays inside)
-    bool mask_ok = W <= 32 && H <= 32;
-    if (mask_ok) {
-      const int wall_off = env.wall_off();
-      for (int j = 1; j < n; ++j) {
-        const uint32_t d = env.desc(j);
-        const int x = env.x(j), y = env.y(j), w = desc_w(d), h = desc_h(d), o = desc_off(d);
-        if (x < 0 || y < 0 || x + w > W || y + h > H) {
-          mask_ok = false;
-          continue;
+    // per-puzzle constants (derived again when an episode restarts on another puzzle)
+    int n, g, w0, h0, ach;
+    uint32_t nn1, aw_xmax, aw_ymax, aw_w, aw_word0, agent_rows, agent_cols, code_idle;
+    bool mask_ok;
+    auto setup = [&]() {  // expects plain positions in env.sm
+      n = env.n();
+      g = env.g();
+      const int W = env.width(), H = env.height();
+      nn1 = 1u + (uint32_t)(n * n);
+      // the agent's wall table (pw_fast.cuh: tab_wall), descriptor cached in registers
+      const uint64_t wd = env.fast(nn1);
+      const uint32_t aw_hi = (uint32_t)(wd >> 32);
+      aw_xmax = aw_hi & 63u;
+      aw_ymax = (aw_hi >> 6) & 0xfffu;
+      aw_w = aw_hi >> 18;
+      aw_word0 = (uint32_t)wd << 1;
+      const uint32_t d0 = env.desc(0);
+      w0 = desc_w(d0);
+      h0 = desc_h(d0);
+      env.masks = false;
+      // mask layout: grid of at most 32 x 32 cells, every movable inside it and off the walls (such a
+      // movable is stopped by the border walls, puzzle.py:160-168, 284-293, so it stays inside)
+      mask_ok = W <= 32 && H <= 32;
+      if (mask_ok) {
+        const int wall_off = env.wall_off();
+        for (int j = 1; j < n; ++j) {
+          const uint32_t d = env.desc(j);
+          const int x = env.x(j), y = env.y(j), w = desc_w(d), h = desc_h(d), o = desc_off(d);
+          if (x < 0 || y < 0 || x + w > W || y + h > H) {
+            mask_ok = false;
+            continue;
+          }
+          for (int r = 0; r < h; ++r) mask_ok = mask_ok && ((env.row(o + r) << x) & env.row(wall_off + y + r)) == 0ull;
         }
-        for (int r = 0; r < h; ++r) mask_ok = mask_ok && ((env.row(o + r) << x) & env.row(wall_off + y + r)) == 0ull;
       }
-    }
-    if (mask_ok) {
-      for (int j = 1; j < n; ++j) {
-        const uint32_t d = env.desc(j);
-        const uint2 v = env.sm[(j - 1) * kOccBlock];
-        env.sm[(j - 1) * kOccBlock] = make_uint2((0xffffffffu >> (32 - desc_h(d))) << v.y,
-                                                 (0xffffffffu >> (32 - desc_w(d))) << v.x);
+      ach = achieved_goals(env);
+      if (mask_ok) {
+        for (int j = 1; j < n; ++j) {
+          const uint32_t d = env.desc(j);
+          const uint2 v = env.sm[(j - 1) * kOccBlock];
+          env.sm[(j - 1) * kOccBlock] = make_uint2((0xffffffffu >> (32 - desc_h(d))) << v.y,
+                                                   (0xffffffffu >> (32 - desc_w(d))) << v.x);
+        }
+        env.masks = true;
       }
-      env.masks = true;
-    }
-    const uint32_t agent_rows = 0xffffffffu >> (32 - min(h0, 32)), agent_cols = 0xffffffffu >> (32 - min(w0, 32));
+      agent_rows = 0xffffffffu >> (32 - min(h0, 32));
+      agent_cols = 0xffffffffu >> (32 - min(w0, 32));
+      code_idle = record_byte(0, ach == g, false);  // the record of a step that moves no movable
+    };
+    setup();
     int& ax = env.ax;
     int& ay = env.ay;
-    int ach = achieved_goals(env);
-    uint32_t code_idle = record_byte(0, ach == g, false);  // the record of a step that moves no movable
+    int ep_steps = kEpisodes ? p.steps[e] : 0;
 
     const int T = p.T;
     uint8_t* const tiles = s_act + warp * (2 * kTileBytes);
@@ -972,9 +1000,10 @@ __global__ void __launch_bounds__(kOccBlock)
     };
     float* rew = kPacked ? nullptr : p.reward + e;
     uint8_t* out8 = kPacked ? p.record + e : p.terminated + e;
+    uint8_t* trunc8 = (kEpisodes && !kPacked && p.truncated) ? p.truncated + e : nullptr;
     uint32_t n_term = 0, n_moved = 0, n_gain = 0, n_invalid = 0;
     constexpr uint32_t kDxBytes = 0x000001ffu, kDyBytes = 0x01ff0000u;  // LEFT, RIGHT, UP, DOWN (puzzle.py:43-50)
-    const uint32_t all_mask_ok = __ballot_sync(0xffffffffu, mask_ok);
+    uint32_t all_mask_ok = __ballot_sync(0xffffffffu, mask_ok);
     const int blocks = (T + 31) / 32;
     issue_block(0);
     for (int blk = 0; blk < blocks; ++blk) {
@@ -1100,14 +1129,41 @@ __global__ void __launch_bounds__(kOccBlock)
           n_gain += (uint32_t)max(dg, 0);
         }
         n_term += code >> 7;
+        bool restart = false;
+        if (kEpisodes) {
+          ++ep_steps;
+          const bool trunc = p.max_steps > 0 && ep_steps >= p.max_steps;  // gym_env.py:223
+          restart = (code >> 7) != 0u || trunc;
+          if (kPacked) {
+            code |= trunc ? 0x40u : 0u;
+          } else if (trunc8) {
+            *trunc8 = trunc ? 1 : 0;
+            trunc8 += p.N;
+          }
+        }
         if (kPacked) {
           *out8 = (uint8_t)code;
         } else {
-          *rew = s_lut[code];
+          *rew = s_lut[code & 0xbfu];
           *out8 = (uint8_t)(code >> 7);
           rew += p.N;
         }
         out8 += p.N;
+        if (kEpisodes && __any_sync(0xffffffffu, restart)) {
+          if (restart) {  // gym_env.py:171-176: a new episode, on a freshly drawn puzzle if asked for
+            if (p.flags & kFlagResample) {
+              const uint32_t episode = p.episode[e] + 1u;
+              p.episode[e] = episode;
+              pid = draw_puzzle(p.seed, e, episode, p.num_puzzles);
+              p.puzzle_id_mut[e] = pid;
+              env.retarget(p.blob + p.puzzle_off[pid]);
+            }
+            env.load_initial();
+            setup();
+            ep_steps = 0;
+          }
+          all_mask_ok = __ballot_sync(0xffffffffu, mask_ok);
+        }
       }
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -1116,6 +1172,7 @@ __global__ void __launch_bounds__(kOccBlock)
     c.dgoals += n_gain;
     c.invalid += n_invalid;
     env.store(p.x, p.y, p.stride, e);
+    if (kEpisodes) p.steps[e] = ep_steps;
   }
   flush_counts(c, p, s_counters);
 }
@@ -1244,13 +1301,26 @@ size_t occ_smem_bytes(int n_max, bool run_ahead) {
 
 }  // namespace
 
-// Serves every plain / packed rollout of the general rule made of whole warps.
+// Serves every plain / packed rollout of the general rule made of whole warps ...
 bool occ_rollout_eligible(const StepParams& p) {
   const auto aligned16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
   const bool plain = p.reward && p.terminated && !p.record;
   const bool packed = p.record && !p.reward && !p.terminated;
   return is_lean(p) && (plain || packed) && (p.N & 31) == 0 && aligned16(p.actions) &&
          (!packed || aligned16(p.record));
+}
+
+// ... and, on the mask kernel, the same output shapes with the episode handling of a vector
+// environment (autoreset, with or without puzzle re-sampling; truncated flags optional).
+bool occ_episodes_eligible(const StepParams& p) {
+  const auto aligned16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+  const bool plain = p.reward && p.terminated && !p.record;
+  const bool packed = p.record && !p.reward && !p.terminated && !p.truncated;
+  const bool resample = (p.flags & kFlagResample) != 0u;
+  const char* mode = getenv("PW_OCC_MODE");
+  return (p.flags & kFlagAutoreset) != 0u && (plain || packed) && !p.dgoals && !p.moved && !p.return_sum &&
+         p.steps != nullptr && (!resample || (p.puzzle_id_mut && p.episode)) && (p.N & 31) == 0 &&
+         aligned16(p.actions) && (mode == nullptr || mode[0] == 'm');
 }
 
 cudaError_t launch_rollout_occ(const StepParams& p_in, cudaStream_t stream) {
@@ -1267,8 +1337,14 @@ cudaError_t launch_rollout_occ(const StepParams& p_in, cudaStream_t stream) {
   const char* mode = getenv("PW_OCC_MODE");
   if (mode == nullptr || mode[0] == 'm') {
     const size_t smem = mask_smem_bytes(p.n_max);
-    if (p.record) k_rollout_mask<true><<<grid, kOccBlock, smem, stream>>>(p);
-    else k_rollout_mask<false><<<grid, kOccBlock, smem, stream>>>(p);
+    const bool episodes = (p.flags & kFlagAutoreset) != 0u;
+    if (p.record) {
+      if (episodes) k_rollout_mask<true, true><<<grid, kOccBlock, smem, stream>>>(p);
+      else k_rollout_mask<true, false><<<grid, kOccBlock, smem, stream>>>(p);
+    } else {
+      if (episodes) k_rollout_mask<false, true><<<grid, kOccBlock, smem, stream>>>(p);
+      else k_rollout_mask<false, false><<<grid, kOccBlock, smem, stream>>>(p);
+    }
     return cudaGetLastError();
   }
   if (mode[0] == 'l') {
@@ -1297,8 +1373,10 @@ cudaError_t configure_occ_kernels() {
   PW_OPT_IN(k_rollout_occ<false>);
   PW_OPT_IN(k_rollout_occ_ra<true>);
   PW_OPT_IN(k_rollout_occ_ra<false>);
-  PW_OPT_IN(k_rollout_mask<true>);
-  PW_OPT_IN(k_rollout_mask<false>);
+  PW_OPT_IN((k_rollout_mask<true, true>));
+  PW_OPT_IN((k_rollout_mask<true, false>));
+  PW_OPT_IN((k_rollout_mask<false, true>));
+  PW_OPT_IN((k_rollout_mask<false, false>));
 #undef PW_OPT_IN
   return err;
 }

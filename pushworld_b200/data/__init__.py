@@ -37,6 +37,31 @@ def solution_plan(key: str) -> str:
     return _bundle()["solutions"][key]["plan"]
 
 
+LEVEL0_PATH = os.path.join(_HERE, "level0.json.gz")
+
+
+@lru_cache(maxsize=1)
+def _level0() -> dict:
+    with gzip.open(LEVEL0_PATH, "rb") as f:
+        return json.loads(f.read().decode("utf-8"))["puzzles"]
+
+
+def level0_keys(category: Optional[str] = None, split: Optional[str] = None) -> List[str]:
+    """Keys (``level0/<category>/<train|test>/<name>``, sorted) of the reference's 15,400 generated
+    level-0 puzzles (benchmark/puzzles/level0.zip, made by python3/src/pushworld/generate.py:136-259);
+    categories: all, base, goals, obstacles, shapes, size, walls."""
+    keys = sorted(_level0().keys())
+    if category is not None:
+        keys = [k for k in keys if k.split("/")[1] == category]
+    if split is not None:
+        keys = [k for k in keys if k.split("/")[2] == split]
+    return keys
+
+
+def level0_text(key: str) -> str:
+    return _level0()[key]
+
+
 def benchmark_texts() -> Dict[str, str]:
     return dict(_bundle()["puzzles"])
 

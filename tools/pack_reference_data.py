@@ -6,11 +6,12 @@ them (``level1/Road Block.pwp``, "all benchmark/puzzles", ...), and
 ``/root/reference`` does not exist on the GPU box.  This script reads
 
     /root/reference/benchmark/puzzles/level{1..4}/*.pwp      (223 puzzles)
+    /root/reference/benchmark/puzzles/level0.zip             (15,400 generated level-0 puzzles)
     /root/reference/benchmark/solutions/**/*.yaml            (223 plans)
     /root/reference/python3/test/puzzles/*.pwp               (14 fixtures)
     /root/reference/cpp/test/puzzles/*.pwp                   (15 fixtures)
 
-and writes ``pushworld_b200/data/benchmark.json.gz`` and
+and writes ``pushworld_b200/data/benchmark.json.gz``, ``pushworld_b200/data/level0.json.gz`` and
 ``tests/golden/test_puzzles.json``.  Run it in the build container only.
 """
 
@@ -65,6 +66,20 @@ def main():
     with gzip.GzipFile(out, "wb", mtime=0) as f:
         f.write(json.dumps(bundle, sort_keys=True).encode())
     print(f"{out}: {len(puzzles)} puzzles, {len(solutions)} plans, {os.path.getsize(out)} bytes")
+
+    # the generated "level 0" set (benchmark/puzzles/level0.zip: 7 categories x (2000 train + 200 test))
+    import zipfile
+
+    level0 = {}
+    with zipfile.ZipFile(os.path.join(root, "level0.zip")) as z:
+        for name in sorted(z.namelist()):
+            if name.endswith(".pwp"):
+                level0[name[:-4]] = z.read(name).decode("utf-8")
+    out = os.path.join(REPO, "pushworld_b200", "data", "level0.json.gz")
+    with gzip.GzipFile(out, "wb", mtime=0) as f:
+        f.write(json.dumps({"source": "google-deepmind/pushworld benchmark/puzzles/level0.zip (Apache-2.0 data)",
+                            "puzzles": level0}, sort_keys=True).encode())
+    print(f"{out}: {len(level0)} level-0 puzzles, {os.path.getsize(out)} bytes")
 
     fixtures = {"python3": {}, "cpp": {}}
     for side, rel in (("python3", "python3/test/puzzles"), ("cpp", "cpp/test/puzzles")):

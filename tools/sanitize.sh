@@ -12,4 +12,4 @@ timeout 1200 $CS --tool racecheck --error-exitcode 1 python -m pytest tests/test
 echo "racecheck exit code $?" >> gpurun_out/sanitizer_racecheck.log
 timeout 900 $CS --tool synccheck --error-exitcode 1 python -m pytest tests/test_gpu_packed.py tests/test_gpu_table.py -x -q > gpurun_out/sanitizer_synccheck.log 2>&1
 echo "synccheck exit code $?" >> gpurun_out/sanitizer_synccheck.log
-tail -4 gpurun_out/sanitizer_memcheck.log gpurun_out/sanitizer_racecheck.log gpurun_out/sanitizer_synccheck.log
+tail -n 4 gpurun_out/sanitizer_memcheck.log gpurun_out/sanitizer_racecheck.log gpurun_out/sanitizer_synccheck.log
