@@ -63,12 +63,32 @@ PW_HD bool tab_pushes(const Env& env, uint32_t pair_index, uint32_t a, int rx, i
   return tab_bit(env.fast32(((uint32_t)pd << 1) + (idx >> 5)), idx);
 }
 
+// tab_pushes for all four actions at once: bit a of the result <=> pusher, moved by action a, pushes
+// j.  The descriptor load and the window test do not depend on the action (the bitmap is indexed
+// (a * Hw + uy) * Ww + ux): successor expansion asks the question for LEFT, RIGHT, UP and DOWN.
+template <class Env>
+PW_HD uint32_t tab_pushes4(const Env& env, uint32_t pair_index, int rx, int ry) {
+  const uint64_t pd = env.fast(pair_index);
+  const uint32_t hi = (uint32_t)(pd >> 32);
+  const uint32_t Ww = hi & 0xffu, Hw = (hi >> 8) & 0x1ffu;
+  const uint32_t ux = (uint32_t)(rx + (int)((hi >> 17) & 0x7fu)), uy = (uint32_t)(ry + (int)(hi >> 24));
+  if (ux >= Ww || uy >= Hw) return 0u;
+  const uint32_t word0 = (uint32_t)pd << 1, plane = Hw * Ww;
+  uint32_t idx = uy * Ww + ux, out = 0u;
+#pragma unroll
+  for (uint32_t a = 0; a < 4u; ++a, idx += plane) out |= tab_bit(env.fast32(word0 + (idx >> 5)), idx) ? (1u << a) : 0u;
+  return out;
+}
+
 // The pushed set of one transition, read from the tables: bit k = object k moves (bit 0 = agent),
 // 0 if the action is invalid or anything in the set is stopped.  Positions are not modified.
 // The scan of a pusher over the other objects is branch-free per object (one pair look-up each);
 // the wall look-ups of the objects it hits come after the scan.
+// `agent_hits` (optional, with have_agent_hits): the objects the agent pushes directly under this
+// action, already known to the caller (successor expansion computes them for all four actions with
+// tab_pushes4); the agent's own scan is then skipped.
 template <class Env>
-PW_HD uint32_t pushed_set_tab(const Env& env, int action) {
+PW_HD uint32_t pushed_set_tab(const Env& env, int action, bool have_agent_hits = false, uint32_t agent_hits = 0u) {
   if ((unsigned)action > 3u) return 0;  // invalid actions are no-ops (counted by the caller)
   const uint32_t a = (uint32_t)action;
   const int n = env.n();
@@ -90,14 +110,18 @@ PW_HD uint32_t pushed_set_tab(const Env& env, int action) {
     // object j's verdict enters at bit 31 and is shifted down once per later object: after the
     // n - 1 objects, bit 32 - n + j; the final shift by 32 - n puts it at bit j
     uint32_t hits = 0;
+    if (have_agent_hits && i == 0) {
+      hits = agent_hits;
+    } else {
 #pragma unroll kUnroll
-    for (int j = 1; j < jend; ++j) {
-      if (Env::kStaticN && j >= n) break;
-      // (the descriptor of the pair (i, i) is zero: an empty window)
-      const bool push = tab_pushes(env, base + (uint32_t)j, a, env.x(j) - xi, env.y(j) - yi);
-      hits = (hits >> 1) | (push ? 0x80000000u : 0u);
+      for (int j = 1; j < jend; ++j) {
+        if (Env::kStaticN && j >= n) break;
+        // (the descriptor of the pair (i, i) is zero: an empty window)
+        const bool push = tab_pushes(env, base + (uint32_t)j, a, env.x(j) - xi, env.y(j) - yi);
+        hits = (hits >> 1) | (push ? 0x80000000u : 0u);
+      }
+      hits = n > 1 ? hits >> (32 - n) : 0u;
     }
-    hits = n > 1 ? hits >> (32 - n) : 0u;
     hits &= ~pushed;
     pushed |= hits;
     frontier |= hits;

@@ -778,11 +778,29 @@ __device__ __forceinline__ void run_expand(Env& env, const ExpandParams& p, int6
   // written straight to its column.  Offset = element index of (object j, successor s); with
   // 32-bit offsets (every launch whose output planes hold < 2^31 elements) an address is one
   // IMAD.WIDE on the FMA pipe instead of an add-with-carry pair on the ALU pipe.
+  // what the agent pushes directly, for all four actions at once (one descriptor load and window
+  // test per object instead of four): bit 4 * j + a <=> the agent, moved by a, pushes object j
+  // (register policies: n <= 8, 4 bits per object in one 32-bit word)
+  constexpr bool use_agent4 = Env::kStaticN > 0 && Env::kStaticN <= 8;
+  uint32_t agent4 = 0;
+  if constexpr (use_agent4) {
+    const int x0 = env.x(0), y0 = env.y(0);
+#pragma unroll
+    for (int j = 1; j < Env::kStaticN; ++j) {
+      if (j >= n) break;
+      agent4 |= tab_pushes4(env, 1u + (uint32_t)j, env.x(j) - x0, env.y(j) - y0) << (4 * j);
+    }
+  }
   auto expand = [&](auto first_offset, auto plane_stride) {
     using Offset = decltype(first_offset);
 #pragma unroll 1
     for (int a = 0; a < 4; ++a) {
-      const uint32_t moved = pushed_set_tab(env, a);
+      uint32_t agent_hits = 0;
+      if constexpr (use_agent4) {
+#pragma unroll
+        for (int j = 1; j < Env::kStaticN; ++j) agent_hits |= ((agent4 >> (4 * j + a)) & 1u) << j;
+      }
+      const uint32_t moved = pushed_set_tab(env, a, use_agent4, agent_hits);
       const int dx = moved ? action_dx(a) : 0, dy = moved ? action_dy(a) : 0;
       const Offset s = (Offset)a * (Offset)p.N + first_offset;
       Offset off = s;
