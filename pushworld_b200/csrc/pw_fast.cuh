@@ -11,7 +11,7 @@
 // All 223 benchmark puzzles together need 0.63 MB of tables (largest: 23 KB).
 //
 // Layout of one puzzle's table F (u64 units, offsets relative to F):
-//   F[0]                 n
+//   F[0]                 n | offset of the initial-state section << 32 (see the end of this list)
 //   F[1 + i*n + j]       pair (pusher i, pushee j >= 1, i != j):
 //                          low word  = offset of the bitmap
 //                          high word = Ww | Hw << 8 | w_j << 17 | h_j << 24
@@ -23,6 +23,11 @@
 //                          high word = xmax | ymax << 6 | W << 18   (xmax = W - w_j, ymax = H - h_j)
 //                        bit ((y * W + x) << 2 | a)  <=>  j at (x, y) is stopped when moved by a;
 //                        positions whose bounding box leaves the grid are never stopped (:557-561)
+//   initial-state section (what an episode restart of pw_occ.cu's mask kernel needs, precomputed):
+//     [0]                low word = 1 if the initial state qualifies for the mask layout (grid of at
+//                        most 32 x 32 cells, every movable inside it and off the walls), bits 8..15 =
+//                        goals achieved in the initial state (puzzle.py:396-407)
+//     [1 + (j - 1)]      object j >= 1 in its initial position: row mask | column mask << 32
 #pragma once
 #include <stdint.h>
 
@@ -219,6 +224,28 @@ inline void build_fast_table(const uint64_t* blob, std::vector<uint64_t>* out) {
                                       ((uint32_t)hj << 24))
                            << 32);
     }
+  }
+  // initial-state section
+  {
+    const int g = (int)(words[kHdrCounts] >> 16);
+    const size_t off = out->size() - start;
+    out->resize(out->size() + (size_t)n, 0ull);  // 1 + (n - 1) words
+    bool ok = W <= 32 && H <= 32;
+    int achieved = 0;
+    for (int j = 1; j < n; ++j) {
+      const uint32_t dj = words[desc_word + 4 * j], init = words[desc_word + 4 * j + 1];
+      const int w = desc_w(dj), h = desc_h(dj), o = desc_off(dj), x = lo16(init), y = hi16(init);
+      if (j <= g && init == words[desc_word + 4 * j + 2]) ++achieved;
+      if (x < 0 || y < 0 || x + w > W || y + h > H || x + w > 32 || y + h > 32) {
+        ok = false;
+        continue;
+      }
+      for (int r = 0; r < h; ++r) ok = ok && ((blob[o + r] << x) & blob[wall_off + y + r]) == 0ull;
+      const uint64_t rm = (0xffffffffull >> (32 - h)) << y, cm = (0xffffffffull >> (32 - w)) << x;
+      (*out)[start + off + 1 + (size_t)(j - 1)] = (rm & 0xffffffffull) | ((cm & 0xffffffffull) << 32);
+    }
+    (*out)[start + off] = (ok ? 1ull : 0ull) | ((uint64_t)achieved << 8);
+    (*out)[start] |= (uint64_t)off << 32;
   }
 }
 

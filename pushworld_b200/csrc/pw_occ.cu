@@ -936,10 +936,9 @@ __global__ void __launch_bounds__(kOccBlock)
     int n, g, w0, h0, ach;
     uint32_t nn1, aw_xmax, aw_ymax, aw_w, aw_word0, agent_rows, agent_cols, code_idle;
     bool mask_ok;
-    auto setup = [&]() {  // expects plain positions in env.sm
+    auto setup_puzzle = [&]() {  // what depends on the puzzle only
       n = env.n();
       g = env.g();
-      const int W = env.width(), H = env.height();
       nn1 = 1u + (uint32_t)(n * n);
       // the agent's wall table (pw_fast.cuh: tab_wall), descriptor cached in registers
       const uint64_t wd = env.fast(nn1);
@@ -951,6 +950,11 @@ __global__ void __launch_bounds__(kOccBlock)
       const uint32_t d0 = env.desc(0);
       w0 = desc_w(d0);
       h0 = desc_h(d0);
+      agent_rows = 0xffffffffu >> (32 - min(h0, 32));
+      agent_cols = 0xffffffffu >> (32 - min(w0, 32));
+    };
+    auto setup_state = [&]() {  // expects plain positions in env.sm
+      const int W = env.width(), H = env.height();
       env.masks = false;
       // mask layout: grid of at most 32 x 32 cells, every movable inside it and off the walls (such a
       // movable is stopped by the border walls, puzzle.py:160-168, 284-293, so it stays inside)
@@ -977,11 +981,32 @@ __global__ void __launch_bounds__(kOccBlock)
         }
         env.masks = true;
       }
-      agent_rows = 0xffffffffu >> (32 - min(h0, 32));
-      agent_cols = 0xffffffffu >> (32 - min(w0, 32));
       code_idle = record_byte(0, ach == g, false);  // the record of a step that moves no movable
     };
-    setup();
+    // a new episode: the initial state, from the section of the puzzle's table that holds it in mask
+    // form (pw_fast.cuh: build_fast_table) when it qualifies -- a restart is then n loads
+    auto restart_episode = [&]() {
+      const uint32_t section = (uint32_t)(env.fast(0u) >> 32);
+      const uint32_t head = (uint32_t)env.fast(section);
+      if (head & 1u) {
+        const uint32_t v0 = env.table_desc(0, 1);
+        env.ax = lo16(v0);
+        env.ay = hi16(v0);
+        for (int j = 1; j < n; ++j) {
+          const uint64_t m = env.fast(section + (uint32_t)j);
+          env.sm[(j - 1) * kOccBlock] = make_uint2((uint32_t)m, (uint32_t)(m >> 32));
+        }
+        env.masks = true;
+        mask_ok = true;
+        ach = (int)((head >> 8) & 0xffu);
+        code_idle = record_byte(0, ach == g, false);
+      } else {
+        env.load_initial();
+        setup_state();
+      }
+    };
+    setup_puzzle();
+    setup_state();
     int& ax = env.ax;
     int& ay = env.ay;
     int ep_steps = kEpisodes ? p.steps[e] : 0;
@@ -1157,9 +1182,9 @@ __global__ void __launch_bounds__(kOccBlock)
               pid = draw_puzzle(p.seed, e, episode, p.num_puzzles);
               p.puzzle_id_mut[e] = pid;
               env.retarget(p.blob + p.puzzle_off[pid]);
+              setup_puzzle();
             }
-            env.load_initial();
-            setup();
+            restart_episode();
             ep_steps = 0;
           }
           all_mask_ok = __ballot_sync(0xffffffffu, mask_ok);
