@@ -124,8 +124,10 @@ PW_API int pw_engine_destroy(PwEngine* engine);
 PW_API int pw_engine_info(const PwEngine* engine, int* num_puzzles, int* n_max, int* max_width,
                    int* max_height);
 
-/* Copies the engine's device-side status block to host: status[0] = number of invalid
- * actions seen since the last poll (then cleared).  SYNCHRONISES `stream`. */
+/* Copies the engine's device-side status block to host (then clears it): status[0] = invalid
+ * actions seen since the last poll, status[1] = visited-set overflows (pw_visited_insert),
+ * status[2] = per-environment puzzle ids outside [0, num_puzzles) (such environments are run on
+ * puzzle 0; the tables are never indexed out of bounds).  SYNCHRONISES `stream`. */
 PW_API int pw_engine_poll(PwEngine* engine, uint64_t status[4], void* stream);
 /* Zeroes the status block on `stream` WITHOUT synchronising (drops counts of earlier launches). */
 PW_API int pw_engine_clear_status(PwEngine* engine, void* stream);

@@ -401,6 +401,8 @@ int pw_reset(PwEngine* e, int64_t n_envs, const int32_t* puzzle_id, int puzzle_u
   ResetParams p{};
   p.blob = e->d_blob;
   p.puzzle_off = e->d_off;
+  p.num_puzzles = (int32_t)e->puzzles.size();
+  p.status = e->d_status;
   p.N = n_envs;
   p.puzzle_id = puzzle_id;
   p.puzzle_uniform = puzzle_uniform;
@@ -431,6 +433,8 @@ int pw_rollout(PwEngine* e, int64_t n_envs, int32_t n_steps, const int32_t* puzz
   StepParams p{};
   p.blob = e->d_blob;
   p.puzzle_off = e->d_off;
+  p.num_puzzles = (int32_t)e->puzzles.size();
+  p.status = e->d_status;
   p.N = n_envs;
   p.T = n_steps;
   p.puzzle_id = puzzle_id;
@@ -457,7 +461,6 @@ int pw_rollout(PwEngine* e, int64_t n_envs, int32_t n_steps, const int32_t* puzz
   p.max_steps = max_steps;
   p.return_sum = return_sum;
   p.counters = reinterpret_cast<unsigned long long*>(counters);
-  p.status = e->d_status;
   p.flags = flags;
   const cudaError_t err = launch_steps(p, n_limit_of(e, puzzle_id, puzzle_uniform),
                                        static_cast<cudaStream_t>(stream));
@@ -481,6 +484,8 @@ int pw_rollout_episodes(PwEngine* e, int64_t n_envs, int32_t n_steps, int32_t* p
   StepParams p{};
   p.blob = e->d_blob;
   p.puzzle_off = e->d_off;
+  p.num_puzzles = (int32_t)e->puzzles.size();
+  p.status = e->d_status;
   p.N = n_envs;
   p.T = n_steps;
   p.puzzle_id = puzzle_id;
@@ -528,6 +533,8 @@ int pw_rollout_packed(PwEngine* e, int64_t n_envs, int32_t n_steps, int32_t* puz
   StepParams p{};
   p.blob = e->d_blob;
   p.puzzle_off = e->d_off;
+  p.num_puzzles = (int32_t)e->puzzles.size();
+  p.status = e->d_status;
   p.N = n_envs;
   p.T = n_steps;
   p.puzzle_id = puzzle_id;
@@ -556,7 +563,6 @@ int pw_rollout_packed(PwEngine* e, int64_t n_envs, int32_t n_steps, int32_t* puz
     p.puzzle_id_mut = puzzle_id;
     p.episode = episode;
     p.seed = seed;
-    p.num_puzzles = (int32_t)e->puzzles.size();
   }
   const cudaError_t err = launch_steps(p, resample ? e->n_max : n_limit_of(e, puzzle_id, puzzle_uniform),
                                        static_cast<cudaStream_t>(stream));
@@ -577,6 +583,8 @@ int pw_step(PwEngine* e, int64_t n_envs, const int32_t* puzzle_id, int puzzle_un
   StepParams p{};
   p.blob = e->d_blob;
   p.puzzle_off = e->d_off;
+  p.num_puzzles = (int32_t)e->puzzles.size();
+  p.status = e->d_status;
   p.N = n_envs;
   p.T = 1;
   p.puzzle_id = puzzle_id;
@@ -617,6 +625,8 @@ int pw_goals(PwEngine* e, int64_t n_envs, const int32_t* puzzle_id, int puzzle_u
   GoalParams p{};
   p.blob = e->d_blob;
   p.puzzle_off = e->d_off;
+  p.num_puzzles = (int32_t)e->puzzles.size();
+  p.status = e->d_status;
   p.N = n_envs;
   p.puzzle_id = puzzle_id;
   p.puzzle_uniform = puzzle_id ? 0 : puzzle_uniform;
@@ -643,6 +653,8 @@ int pw_expand(PwEngine* e, int64_t n_states, const int32_t* puzzle_id, int puzzl
   ExpandParams p{};
   p.blob = e->d_blob;
   p.puzzle_off = e->d_off;
+  p.num_puzzles = (int32_t)e->puzzles.size();
+  p.status = e->d_status;
   p.N = n_states;
   p.puzzle_id = puzzle_id;
   p.puzzle_uniform = puzzle_id ? 0 : puzzle_uniform;
@@ -676,6 +688,8 @@ int pw_expand_indexed(PwEngine* e, int64_t n_states, int puzzle, const int64_t* 
   ExpandParams p{};
   p.blob = e->d_blob;
   p.puzzle_off = e->d_off;
+  p.num_puzzles = (int32_t)e->puzzles.size();
+  p.status = e->d_status;
   p.N = n_states;
   p.puzzle_id = nullptr;
   p.puzzle_uniform = puzzle;
@@ -711,6 +725,8 @@ int pw_visited_insert(PwEngine* e, int puzzle, const int32_t* x, const int32_t* 
   VisitedParams p{};
   p.blob = e->d_blob;
   p.puzzle_off = e->d_off;
+  p.num_puzzles = (int32_t)e->puzzles.size();
+  p.status = e->d_status;
   p.puzzle = puzzle;
   p.x = x;
   p.y = y;
@@ -789,6 +805,8 @@ static int render_common(PwEngine* e, int64_t n_envs, const int32_t* puzzle_id, 
   RenderParams p{};
   p.blob = e->d_blob;
   p.puzzle_off = e->d_off;
+  p.num_puzzles = (int32_t)e->puzzles.size();
+  p.status = e->d_status;
   p.N = n_envs;
   p.puzzle_id = puzzle_id;
   p.puzzle_uniform = puzzle_id ? 0 : puzzle_uniform;
@@ -835,6 +853,8 @@ int pw_step_render(PwEngine* e, int64_t n_envs, const int32_t* puzzle_id, int pu
   StepParams p{};
   p.blob = e->d_blob;
   p.puzzle_off = e->d_off;
+  p.num_puzzles = (int32_t)e->puzzles.size();
+  p.status = e->d_status;
   p.N = n_envs;
   p.T = 1;
   p.puzzle_id = puzzle_id;

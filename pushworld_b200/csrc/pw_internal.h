@@ -5,6 +5,18 @@
 
 namespace pw {
 
+#if defined(__CUDACC__)
+// A per-environment puzzle id as the kernels use it: ids outside the engine's puzzles select puzzle
+// 0 and are counted in status word 2 (pw_engine_poll) instead of indexing the tables out of bounds.
+__device__ __forceinline__ int checked_puzzle_id(int pid, int num_puzzles, unsigned long long* status) {
+  if ((unsigned)pid >= (unsigned)num_puzzles) {
+    if (status) atomicAdd(&status[2], 1ull);
+    return 0;
+  }
+  return pid;
+}
+#endif
+
 constexpr uint32_t kFlagAutoreset = 1u;
 constexpr uint32_t kFlagResample = 2u;  // autoreset draws a new puzzle (pw_rollout_episodes)
 
@@ -63,16 +75,18 @@ struct StepParams {
   unsigned long long* counters;  // [4] or nullptr
   unsigned long long* status;    // engine status block
   uint32_t flags;
+  int32_t num_puzzles;
   // pw_rollout_episodes only
   int32_t* puzzle_id_mut;
   uint32_t* episode;
   uint64_t seed;
-  int32_t num_puzzles;
 };
 
 struct ExpandParams {
   const uint64_t* blob;
   const uint32_t* puzzle_off;
+  int32_t num_puzzles;
+  unsigned long long* status;
   int64_t N;
   const int32_t* puzzle_id;
   int32_t puzzle_uniform;
@@ -92,6 +106,8 @@ struct ExpandParams {
 struct ResetParams {
   const uint64_t* blob;
   const uint32_t* puzzle_off;
+  int32_t num_puzzles;
+  unsigned long long* status;
   int64_t N;
   const int32_t* puzzle_id;
   int32_t puzzle_uniform;
@@ -106,6 +122,8 @@ struct ResetParams {
 struct GoalParams {
   const uint64_t* blob;
   const uint32_t* puzzle_off;
+  int32_t num_puzzles;
+  unsigned long long* status;
   int64_t N;
   const int32_t* puzzle_id;
   int32_t puzzle_uniform;
@@ -119,6 +137,7 @@ struct GoalParams {
 struct VisitedParams {
   const uint64_t* blob;
   const uint32_t* puzzle_off;
+  int32_t num_puzzles;
   int32_t puzzle;
   const int32_t* x;
   const int32_t* y;
@@ -146,6 +165,8 @@ struct NoveltyParams {
 struct RenderParams {
   const uint64_t* blob;
   const uint32_t* puzzle_off;
+  int32_t num_puzzles;
+  unsigned long long* status;
   int64_t N;
   const int32_t* puzzle_id;
   int32_t puzzle_uniform;

@@ -702,7 +702,7 @@ __global__ void __launch_bounds__(kBlock, MIN_BLOCKS)
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   StepCounts c;
   if (e < p.N) {
-    const int pid = p.puzzle_id ? p.puzzle_id[e] : p.puzzle_uniform;
+    const int pid = p.puzzle_id ? checked_puzzle_id(p.puzzle_id[e], p.num_puzzles, p.status) : p.puzzle_uniform;
     const GlobalTable tbl{p.blob + p.puzzle_off[pid]};
     Board<NMAX, Word> s;
     BoardSimMixed<NMAX, Word> sim{s, nullptr, 0u, 0};
@@ -751,7 +751,7 @@ __global__ void __launch_bounds__(kBlock)
   __syncthreads();
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool active = e < p.N;
-  const int pid = (active && p.puzzle_id) ? p.puzzle_id[e] : p.puzzle_uniform;
+  const int pid = (active && p.puzzle_id) ? checked_puzzle_id(p.puzzle_id[e], p.num_puzzles, p.status) : p.puzzle_uniform;
   const GlobalTable table{p.blob + p.puzzle_off[pid]};
   if constexpr (NMAX > 0) {
     RegEnv<NMAX, GlobalTable> env;
@@ -849,7 +849,8 @@ __global__ void __launch_bounds__(kBlock) k_expand_mixed(const ExpandParams p) {
   extern __shared__ uint64_t smem[];
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= p.N) return;
-  const GlobalTable table{p.blob + p.puzzle_off[p.puzzle_id ? p.puzzle_id[e] : p.puzzle_uniform]};
+  const GlobalTable table{
+      p.blob + p.puzzle_off[p.puzzle_id ? checked_puzzle_id(p.puzzle_id[e], p.num_puzzles, p.status) : p.puzzle_uniform]};
   if constexpr (NMAX > 0) {
     RegEnv<NMAX, GlobalTable> env;
     env.init(table);
@@ -869,7 +870,7 @@ __global__ void __launch_bounds__(kBlock) k_reset(const ResetParams p) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= p.N) return;
   if (p.reset_mask && p.reset_mask[e] == 0) return;
-  const int pid = p.puzzle_id ? p.puzzle_id[e] : p.puzzle_uniform;
+  const int pid = p.puzzle_id ? checked_puzzle_id(p.puzzle_id[e], p.num_puzzles, p.status) : p.puzzle_uniform;
   const GlobalTable t{p.blob + p.puzzle_off[pid]};
   const int n = (int)(t.word(kHdrCounts) & 0xffffu);
   const int desc_word = (int)t.word(kHdrObjOff) * 2;
@@ -890,7 +891,7 @@ __global__ void __launch_bounds__(kBlock) k_reset(const ResetParams p) {
 __global__ void __launch_bounds__(kBlock) k_goals(const GoalParams p) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= p.N) return;
-  const int pid = p.puzzle_id ? p.puzzle_id[e] : p.puzzle_uniform;
+  const int pid = p.puzzle_id ? checked_puzzle_id(p.puzzle_id[e], p.num_puzzles, p.status) : p.puzzle_uniform;
   const GlobalTable t{p.blob + p.puzzle_off[pid]};
   const int g = (int)(t.word(kHdrCounts) >> 16);
   const int desc_word = (int)t.word(kHdrObjOff) * 2;

@@ -361,7 +361,7 @@ __global__ void __launch_bounds__(kOccBlock)
   const int64_t e = (int64_t)blockIdx.x * kOccBlock + tid;
   StepCounts c;
   if (e < p.N) {  // whole warps (the launcher requires N % 32 == 0)
-    const int pid = p.puzzle_id ? p.puzzle_id[e] : p.puzzle_uniform;
+    const int pid = p.puzzle_id ? checked_puzzle_id(p.puzzle_id[e], p.num_puzzles, p.status) : p.puzzle_uniform;
     OccEnv env;
     env.init(GlobalTable{p.blob + p.puzzle_off[pid]}, s_posx + tid, s_posy + tid);
     env.load(p.x, p.y, p.stride, e);
@@ -646,7 +646,7 @@ __global__ void __launch_bounds__(kOccBlock)
   const int64_t e = (int64_t)blockIdx.x * kOccBlock + tid;
   StepCounts c;
   if (e < p.N) {  // whole warps (the launcher requires N % 32 == 0)
-    const int pid = p.puzzle_id ? p.puzzle_id[e] : p.puzzle_uniform;
+    const int pid = p.puzzle_id ? checked_puzzle_id(p.puzzle_id[e], p.num_puzzles, p.status) : p.puzzle_uniform;
     OccEnv env;
     env.init(GlobalTable{p.blob + p.puzzle_off[pid]}, s_posx + tid, s_posy + tid);
     env.load(p.x, p.y, p.stride, e);
@@ -928,7 +928,7 @@ __global__ void __launch_bounds__(kOccBlock)
   const int64_t e = (int64_t)blockIdx.x * kOccBlock + tid;
   StepCounts c;
   if (e < p.N) {  // whole warps (the launcher requires N % 32 == 0)
-    int pid = p.puzzle_id ? p.puzzle_id[e] : p.puzzle_uniform;
+    int pid = p.puzzle_id ? checked_puzzle_id(p.puzzle_id[e], p.num_puzzles, p.status) : p.puzzle_uniform;
     MaskEnv env;
     env.init(GlobalTable{p.blob + p.puzzle_off[pid]}, s_obj + tid);
     env.load(p.x, p.y, p.stride, e);
@@ -1223,7 +1223,7 @@ __global__ void __launch_bounds__(kWarpEnvBlock) k_rollout_warp_per_env(const __
   const int64_t e = (int64_t)blockIdx.x * (kWarpEnvBlock / 32) + (threadIdx.x >> 5);
   StepCounts c;
   if (e < p.N) {
-    const int pid = p.puzzle_id ? p.puzzle_id[e] : p.puzzle_uniform;
+    const int pid = p.puzzle_id ? checked_puzzle_id(p.puzzle_id[e], p.num_puzzles, p.status) : p.puzzle_uniform;
     EnvBase<GlobalTable> env;
     env.init_header(GlobalTable{p.blob + p.puzzle_off[pid]});
     const int n = env.n(), g = env.g();

@@ -146,7 +146,9 @@ __global__ void __launch_bounds__(kRenderBlock) k_render(const RenderParams p) {
   }
   int cur_pid = -1, W = 0, H = 0, n = 0, img_h = 0, img_w = 0, pad_top = 0, pad_left = 0;
   for (int64_t e = blockIdx.x; e < p.N; e += G) {
-    const int pid = p.puzzle_id ? p.puzzle_id[e] : p.puzzle_uniform;
+    // (every thread of the CTA reads the id; thread 0 reports a bad one)
+    const int pid = p.puzzle_id ? checked_puzzle_id(p.puzzle_id[e], p.num_puzzles, threadIdx.x == 0 ? p.status : nullptr)
+                                : p.puzzle_uniform;
     if (pid != cur_pid) {  // block-uniform branch
       cur_pid = pid;
       const uint64_t* g_tbl = p.blob + p.puzzle_off[pid];

@@ -110,6 +110,7 @@ class Engine:
         self.n_max = max(p.num_objects for p in self.parsed)
         self.max_width = max(p.width for p in self.parsed)
         self.max_height = max(p.height for p in self.parsed)
+        self.bad_puzzle_ids = 0  # out-of-range ids seen by polls that were asked about something else
 
     def close(self) -> None:
         if getattr(self, "_h", None):
@@ -447,7 +448,17 @@ class Engine:
         """(invalid actions, visited-table overflows) since the last poll (synchronises)."""
         status = (ctypes.c_uint64 * 4)()
         _lib.check(self._lib.pw_engine_poll(self._h, status, self._stream()))
+        self.bad_puzzle_ids += int(status[2])
         return int(status[0]), int(status[1])
+
+    def poll_bad_puzzle_ids(self) -> int:
+        """Number of per-environment puzzle ids outside ``[0, num_puzzles)`` the kernels have seen
+        since the last call (such environments are run on puzzle 0 instead of reading the tables
+        out of bounds).  Synchronises; also clears the other status words."""
+        status = (ctypes.c_uint64 * 4)()
+        _lib.check(self._lib.pw_engine_poll(self._h, status, self._stream()))
+        count, self.bad_puzzle_ids = self.bad_puzzle_ids + int(status[2]), 0
+        return count
 
     def _render_out(self, n, dtype, ppc, pad_cells, out):
         tdtype = torch.float32 if dtype == "float32" else torch.uint8
@@ -519,4 +530,5 @@ class Engine:
         """Number of out-of-range actions seen since the last poll (synchronises)."""
         status = (ctypes.c_uint64 * 4)()
         _lib.check(self._lib.pw_engine_poll(self._h, status, self._stream()))
+        self.bad_puzzle_ids += int(status[2])
         return int(status[0])

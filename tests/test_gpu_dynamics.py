@@ -684,3 +684,28 @@ def test_plain_rollouts_on_the_general_rule(setup, golden):
         assert np.array_equal(r1.cpu().numpy(), np.repeat(reward[:, e:e + 1].cpu().numpy(), 32, axis=1)), key
         assert np.array_equal(t1.cpu().numpy(), np.repeat(term[:, e:e + 1].cpu().numpy(), 32, axis=1)), key
         assert np.array_equal(xy1.cpu().numpy()[:, :, 0], xy.cpu().numpy()[:, :, e]), key
+
+
+def test_out_of_range_puzzle_ids_are_counted_not_dereferenced(setup):
+    """Direct Engine / C-ABI callers can pass any int32 as a puzzle id: the kernels run such an
+    environment on puzzle 0 and count it (status word 2) instead of reading the tables out of bounds."""
+    engine, keys = setup
+    n = 96
+    pid = torch.zeros(n, dtype=torch.int32, device="cuda")
+    pid[5], pid[40], pid[77] = -3, len(keys), 2**30
+    xy = engine.new_state(n)
+    engine.reset(xy, pid)
+    ok = engine.new_state(n)
+    engine.reset(ok, torch.zeros(n, dtype=torch.int32, device="cuda"))
+    assert torch.equal(xy, ok)
+    assert engine.poll_bad_puzzle_ids() == 3
+    actions = torch.randint(0, 4, (40, n), dtype=torch.uint8, device="cuda")
+    reward = torch.empty((40, n), dtype=torch.float32, device="cuda")
+    term = torch.empty((40, n), dtype=torch.uint8, device="cuda")
+    engine.rollout(xy, pid, actions, reward=reward, terminated=term)
+    engine.step(xy, pid, actions[0])
+    engine.expand(xy, pid)
+    engine.render(xy, pid)
+    torch.cuda.synchronize()
+    assert engine.poll_bad_puzzle_ids() == 12
+    assert engine.poll_bad_puzzle_ids() == 0
