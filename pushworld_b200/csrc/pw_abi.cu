@@ -319,12 +319,13 @@ int pw_engine_create(const void* blob, size_t blob_bytes, const uint32_t* offset
       if (err == cudaSuccess) err = cudaMalloc(&tv.hash_keys, sizeof(unsigned long long) * (size_t)tv.hash_cap);
       if (err == cudaSuccess) err = cudaMalloc(&tv.hash_vals, sizeof(uint32_t) * (size_t)tv.hash_cap);
       if (err == cudaSuccess) err = cudaMemset(tv.hash_keys, 0, sizeof(unsigned long long) * (size_t)tv.hash_cap);
-      if (err == cudaSuccess) tv.n_states = build_state_table(e->d_blob, packed_off[(size_t)p], tv, max_states, &err);
+      if (err == cudaSuccess) tv.n_states = build_state_table(e->d_blob, packed_off[(size_t)p], &tv, max_states, &err);
       if (err != cudaSuccess || tv.n_states == 0) {
         cudaFree(tv.keys);
         cudaFree(tv.table);
         cudaFree(tv.hash_keys);
         cudaFree(tv.hash_vals);
+        if (tv.pairs) cudaFree(tv.pairs);
         tv = StateTableView{};
       }
       e->state_tables[(size_t)p] = tv;
@@ -352,6 +353,7 @@ int pw_engine_destroy(PwEngine* e) {
     if (tv.table) cudaFree(tv.table);
     if (tv.hash_keys) cudaFree(tv.hash_keys);
     if (tv.hash_vals) cudaFree(tv.hash_vals);
+    if (tv.pairs) cudaFree(tv.pairs);
   }
   delete e;
   return PW_OK;

@@ -40,6 +40,12 @@ struct StateTableView {
   int32_t hash_cap;               // power of two
   int32_t key_bits;               // bits per object in a packed state (cell index y * W + x)
   int32_t goals;                  // the puzzle's number of goal objects
+  // States are numbered so that the ones with every goal achieved come last: state s is terminal
+  // (PushWorldPuzzle.is_goal_state) <=> s >= n_off.
+  int32_t n_off;
+  // [n_states * 16] two-step entries (state, a1, a2) -> successor * 8 | after-a1-terminal << 2 | steps that moved
+  // (0..2); nullptr when the puzzle has several goal objects or too many states for a CTA to stage them
+  uint16_t* pairs;
 };
 
 struct StepParams {
@@ -195,7 +201,7 @@ cudaError_t launch_rollout_occ(const StepParams& p, cudaStream_t stream);
 cudaError_t configure_occ_kernels();
 // pw_table.cu: rollouts of a small puzzle on its reachable-state transition table
 int state_table_max_states();
-int build_state_table(const uint64_t* d_blob, uint32_t puzzle_off, const StateTableView& tv, int max_states,
+int build_state_table(const uint64_t* d_blob, uint32_t puzzle_off, StateTableView* tv, int max_states,
                       cudaError_t* err);
 bool table_rollout_eligible(const StepParams& p);
 cudaError_t launch_rollout_table(const StepParams& p, cudaStream_t stream);

@@ -36,7 +36,7 @@ __device__ __forceinline__ uint32_t warp_sum(uint32_t v) {
 // T fused steps of one environment per thread (pw_steps.cuh) + block-level counter flush.
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void flush_counts(const StepCounts& c, const StepParams& p,
-                                             uint32_t* s_counters) {
+                                             uint32_t* s_counters, int envs_per_thread = 1) {
   // Launches without a counter vector (pw_step, pw_step_render) only report invalid actions, which
   // are rare: one block-wide vote decides whether anything has to be reduced at all.
   if (!p.counters && !__syncthreads_or(c.invalid != 0u)) return;
@@ -52,9 +52,9 @@ __device__ __forceinline__ void flush_counts(const StepCounts& c, const StepPara
     __syncthreads();
     if (threadIdx.x == 0) {
       if (p.counters) {
-        const int64_t first = (int64_t)blockIdx.x * blockDim.x;
-        const int64_t rest = p.N - first;
-        const int64_t live = rest < (int64_t)blockDim.x ? rest : (int64_t)blockDim.x;
+        const int64_t per_cta = (int64_t)blockDim.x * envs_per_thread;
+        const int64_t rest = p.N - (int64_t)blockIdx.x * per_cta;
+        const int64_t live = rest < per_cta ? rest : per_cta;
         atomicAdd(&p.counters[0], (unsigned long long)(live > 0 ? live : 0) * (unsigned long long)p.T);
         if (s_counters[0]) atomicAdd(&p.counters[1], (unsigned long long)s_counters[0]);
         if (s_counters[1]) atomicAdd(&p.counters[2], (unsigned long long)s_counters[1]);

@@ -4,7 +4,7 @@
     ncu --set full --clock-control none --import-source on -k regex:<kernel> -s 2 -c 1 \
         -o gpurun_out/prof_<name> python tools/profile_kernels.py <name>
 
-names: step1 (pw_step T=1, Road Block 2^18), mixed (cfg3 rollout T=64), expand (cfg4, 2M states),
+names: step1 (pw_step T=1, Road Block 2^18), mixed (cfg3 rollout T=256), expand (cfg4, 2M states),
 render_f32 / render_u8 / step_render_f32 (cfg5, 2^14 frames).
 """
 import os

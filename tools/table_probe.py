@@ -27,9 +27,20 @@ record = torch.empty((T, n), dtype=torch.uint8, device="cuda")
 xy = eng.new_state(n)
 eng.reset(xy, 0)
 xy0 = xy.clone()
-for wide in (False, True):
-    if wide: os.environ["PW_TABLE_WIDE"] = "1"
-    for block in [0, 128, 256, 384, 448, 512, 640, 768, 896, 928, 960, 1024]:
+VARIANTS = {
+    "quad": {},                                             # two-step table, four environments per thread
+    "pairs": {"PW_NO_QUAD": "1"},                           # two-step table, one environment per thread
+    "compact1": {"PW_NO_PAIRS": "1", "PW_TABLE_CTAS": "1"},  # one-step compact entries, 64 registers
+    "compact2": {"PW_NO_PAIRS": "1", "PW_TABLE_CTAS": "2"},  # ... 32 registers, two CTAs per SM
+    "wide": {"PW_TABLE_WIDE": "1"},                         # one-step 32-bit entries + reward table
+}
+only = sys.argv[1:] or list(VARIANTS)
+for name in only:
+    for k in ("PW_NO_QUAD", "PW_NO_PAIRS", "PW_TABLE_CTAS", "PW_TABLE_WIDE"):
+        os.environ.pop(k, None)
+    os.environ.update(VARIANTS[name])
+    blocks = [0, 128, 192, 256, 320, 384, 448, 512] if name == "quad" else [0, 448, 512, 896, 1024]
+    for block in blocks:
         os.environ["PW_TABLE_BLOCK"] = str(block)
         def run():
             xy.copy_(xy0)
@@ -38,5 +49,5 @@ for wide in (False, True):
             xy.copy_(xy0)
             eng.rollout_packed(xy, 0, actions, record)
         ms, msp = time_ms(run), time_ms(run_p)
-        print(json.dumps({"wide": wide, "block": block, "plain_ms": round(ms, 4), "plain_frac": round(n*T*6.047/ms/1e6/6530.3, 3),
+        print(json.dumps({"variant": name, "block": block, "plain_ms": round(ms, 4), "plain_frac": round(n*T*6.047/ms/1e6/6530.3, 3),
                           "packed_ms": round(msp, 4)}), flush=True)
