@@ -33,7 +33,7 @@ PUZZLE_KEY = "level1/Road Block"
 N_ENVS = 1 << 18
 T_STEPS = 1024
 ACTION_SEED = 1234
-ROLLOUT_KERNEL = "k_rollout_table<plain, compact> (pw_rollout on the reachable-state transition table)"
+ROLLOUT_KERNEL = "k_rollout_pairs4<plain> (pw_rollout on the two-step reachable-state table, four environments per thread)"
 
 
 def _workload_config(n_gpus: int) -> dict:
