@@ -107,3 +107,61 @@ def test_states_outside_the_table_and_invalid_actions():
         assert tab.poll_invalid_actions() == 33
         for a, b in zip(got, base):
             assert torch.equal(a, b), packed
+
+
+VARIANTS = {
+    "quad": {},  # two-step table, four environments per thread (needs N % 128 == 0, aligned outputs)
+    "pairs": {"PW_NO_QUAD": "1"},  # two-step table, one environment per thread
+    "compact-1cta": {"PW_NO_PAIRS": "1", "PW_TABLE_CTAS": "1"},  # one-step compact entries
+    "compact-2cta": {"PW_NO_PAIRS": "1", "PW_TABLE_CTAS": "2"},
+    "wide": {"PW_TABLE_WIDE": "1"},  # one-step 32-bit entries (the form puzzles with several goals use)
+}
+
+
+@pytest.mark.parametrize("variant", list(VARIANTS))
+@pytest.mark.parametrize("n,T", [(4096, 77), (4096 + 32, 48), (128, 1), (256, 16)])
+def test_every_table_kernel_variant(variant, n, T):
+    """All table kernels (the default picks the first that fits the launch) against the engine without
+    tables: odd / partial action tiles, out-of-range actions inside full and partial tiles, batch sizes
+    that are not a multiple of 128 (the four-environments-per-thread kernel hands over to the
+    one-environment one), outputs that are not 16-byte aligned."""
+    from pushworld_b200 import data
+
+    text = data.puzzle_text("level1/Road Block")
+    tab, ref = _engine(text, True), _engine(text, False)
+    gen = torch.Generator(device="cuda").manual_seed(1000 + n + T)
+    actions = torch.randint(0, 4, (T, n), dtype=torch.uint8, device="cuda", generator=gen)
+    bad = 0
+    if T >= 16:
+        actions[3, 5] = 4
+        actions[T - 1, n - 1] = 255
+        actions[T // 2, 64:96] = 9
+        bad = 34
+    xy0 = tab.new_state(n)
+    tab.reset(xy0, 0)
+    tab.rollout(xy0, 0, torch.randint(0, 4, (40, n), dtype=torch.uint8, device="cuda", generator=gen))  # spread out
+    base = _run(ref, xy0, actions, False)
+    assert ref.poll_invalid_actions() == bad
+    keys = ("PW_NO_QUAD", "PW_NO_PAIRS", "PW_TABLE_CTAS", "PW_TABLE_WIDE")
+    saved = {k: os.environ.pop(k, None) for k in keys}
+    try:
+        os.environ.update(VARIANTS[variant])
+        for packed in (False, True):
+            got = _run(tab, xy0, actions, packed)
+            assert tab.poll_invalid_actions() == bad
+            for a, b in zip(got, base):
+                assert torch.equal(a, b), (variant, packed)
+        # outputs at an odd element offset (not 16-byte aligned): the vector stores must not be used
+        T2 = actions.shape[0]
+        buf_r = torch.zeros(T2 * n + 1, dtype=torch.float32, device="cuda")
+        buf_t = torch.zeros(T2 * n + 1, dtype=torch.uint8, device="cuda")
+        reward, term = buf_r[1:].view(T2, n), buf_t[1:].view(T2, n)
+        xy = xy0.clone()
+        tab.rollout(xy, 0, actions, reward=reward, terminated=term)
+        tab.poll_invalid_actions()
+        assert torch.equal(reward, base[1]) and torch.equal(term, base[2]) and torch.equal(xy, base[0])
+    finally:
+        for k in keys:
+            os.environ.pop(k, None)
+            if saved[k] is not None:
+                os.environ[k] = saved[k]
