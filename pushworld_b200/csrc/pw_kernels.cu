@@ -771,6 +771,7 @@ __global__ void __launch_bounds__(kBlock)
 // ------------------------------------------------------------------------------------------
 template <class Env>
 __device__ __forceinline__ void run_expand(Env& env, const ExpandParams& p, int64_t e) {
+  const unsigned live = __activemask();  // the warp's lanes that have a state (converged here)
   env.load(p.x_in, p.y_in, p.stride_in, p.index ? p.index[e] : e);
   const int g = env.g(), n = env.n();
   const int jend = Env::kStaticN ? Env::kStaticN : n;
@@ -797,23 +798,42 @@ __device__ __forceinline__ void run_expand(Env& env, const ExpandParams& p, int6
     for (int a = 0; a < 4; ++a) {
       uint32_t agent_hits = 0;
       if constexpr (use_agent4) {
-#pragma unroll
-        for (int j = 1; j < Env::kStaticN; ++j) agent_hits |= ((agent4 >> (4 * j + a)) & 1u) << j;
+        // bit 4 j + a of agent4 -> bit j: the nibbles' selected bits gathered by three shift-or-mask rounds
+        uint32_t t = (agent4 >> a) & 0x11111111u;
+        t = (t | (t >> 3)) & 0x03030303u;
+        t = (t | (t >> 6)) & 0x000f000fu;
+        agent_hits = (t | (t >> 12)) & 0xffu;
       }
       const uint32_t moved = pushed_set_tab(env, a, use_agent4, agent_hits);
+      // the closure's data-dependent loops leave the lanes apart; without this the stores below ran with a
+      // quarter of the lanes (ncu: 8 of 32 active)
+      __syncwarp(live);
       const int dx = moved ? action_dx(a) : 0, dy = moved ? action_dy(a) : 0;
       const Offset s = (Offset)a * (Offset)p.N + first_offset;
       Offset off = s;
-      int at_goal = 0;
 #pragma unroll
       for (int j = 0; j < jend; ++j) {
         if (Env::kStaticN && j >= n) break;
         const bool m = (moved >> j) & 1u;
-        const int x = env.x(j) + (m ? dx : 0), y = env.y(j) + (m ? dy : 0);
-        p.x_out[off] = x;
-        p.y_out[off] = y;
+        p.x_out[off] = env.x(j) + (m ? dx : 0);
+        p.y_out[off] = env.y(j) + (m ? dy : 0);
         off += plane_stride;
-        if (j >= 1 && j <= g) at_goal += (x == env.goal_x(j - 1) && y == env.goal_y(j - 1)) ? 1 : 0;
+      }
+      // goal objects are objects 1..g: a short loop with a uniform exit instead of a test on every object
+      int at_goal = 0;
+      auto goal_test = [&](const int j) {
+        const bool m = (moved >> j) & 1u;
+        const int x = env.x(j) + (m ? dx : 0), y = env.y(j) + (m ? dy : 0);
+        at_goal += (x == env.goal_x(j - 1) && y == env.goal_y(j - 1)) ? 1 : 0;
+      };
+      if constexpr (Env::kStaticN > 0) {
+#pragma unroll
+        for (int j = 1; j < Env::kStaticN; ++j) {
+          if (j > g) break;
+          goal_test(j);
+        }
+      } else {
+        for (int j = 1; j <= g; ++j) goal_test(j);
       }
       if (p.moved) p.moved[s] = moved;
       if (p.goal) p.goal[s] = at_goal == g ? 1 : 0;  // pushworld_puzzle.cc:462-469
