@@ -533,14 +533,17 @@ def run_ours(args) -> None:
     torch.cuda.synchronize()
     sampler.mark_begin()
     start.record()
+    host_t0 = time.perf_counter()
     for k in range(args.steps):
         one_step(k, *kernel_events[k])
+    host_issue_ms = (time.perf_counter() - host_t0) * 1e3 / max(args.steps, 1)  # launch work of one step, host side
     torch.cuda.current_stream(dev).wait_stream(side)  # the last all-reduce is part of the job
     stop.record()
     torch.cuda.synchronize()
     sampler.mark_end()
     distributed.barrier()
     elapsed_ms = distributed.max_over_ranks(start.elapsed_time(stop), dev)
+    host_issue_ms = distributed.max_over_ranks(host_issue_ms, dev)
     total_env_steps = int(totals[0].item())
     assert total_env_steps == world * args.steps * N_ENVS * T_STEPS, total_env_steps
     value = total_env_steps / (elapsed_ms * 1e-3)
@@ -663,6 +666,7 @@ def run_ours(args) -> None:
         "steps": args.steps,
         "warmup": args.warmup,
         "ms_per_step": elapsed_ms / args.steps,
+        "host_issue_ms_per_step": host_issue_ms,  # max over ranks: the launch work of a step on the host
         "higher_is_better": True,
         "scaling": "weak",
         "vs_baseline": None,
