@@ -904,17 +904,41 @@ __device__ __forceinline__ uint32_t shift_mask(uint32_t m, int d) { return d > 0
 // kEpisodes: step counter, truncation (gym_env.py:223) and -- after a terminated or truncated step -- a
 // restart from the initial state, of a freshly drawn puzzle under pw_rollout_episodes' flag
 // (gym_env.py:171-176 on the device); the per-puzzle constants below are then derived again.
-template <bool kPacked, bool kEpisodes>
+//
+// kCta (PW_MASK_CTA=1, a measured alternative -- slower): the closure is resolved by
+// the CTA instead of the warp.  In lock-step, ~99 % of the warp-steps
+// run the exact look-ups for the ~4 lanes that have a prefilter candidate and 62 % run a second closure
+// round for 1-2 lanes.  Here a step has three phases separated by two barriers: (A) every thread does
+// the common part and the agent's prefilter; the 13 % of the environments with a candidate post
+// themselves (candidates, action, agent position) in a shared-memory list; (B) the first `count`
+// threads of the CTA take one posted environment each -- its masks are in shared memory, its
+// tables behind a pointer posted at set-up -- and resolve its closure completely (exact look-ups,
+// further rounds, displacement of the masks, goal delta), all lanes of the resolving warp busy;
+// (C) the owners read the verdict back and write the step's outputs.
+struct FastView {  // the collision tables of a posted environment (what tab_pushes / tab_wall read)
+  const uint64_t* ft;
+  __device__ __forceinline__ uint64_t fast(uint32_t k) const { return __ldg(ft + k); }
+  __device__ __forceinline__ uint32_t fast32(uint32_t k) const { return __ldg(reinterpret_cast<const uint32_t*>(ft) + k); }
+};
+
+template <bool kPacked, bool kEpisodes, bool kCta>
 __global__ void __launch_bounds__(kOccBlock)
     k_rollout_mask(const __grid_constant__ StepParams p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   __shared__ uint32_t s_counters[4];
-  // dynamic shared memory: object masks / positions | action tiles | reward table
+  __shared__ uint32_t s_posted[2];  // kCta: environments posted in the current / next step
+  // dynamic shared memory: object masks / positions | action tiles | reward table | kCta: mail boxes, lists
   uint2* s_obj = reinterpret_cast<uint2*>(smem_raw);
   const int pos_rows = p.n_max > 1 ? p.n_max - 1 : 1;
   uint8_t* s_act = reinterpret_cast<uint8_t*>(s_obj + pos_rows * kOccBlock);
   float* s_lut = reinterpret_cast<float*>(s_act + (kOccBlock / 32) * 2 * kTileBytes);
+  uint4* s_mail = reinterpret_cast<uint4*>(s_lut + 256);  // in: candidates, action, ax, ay; out: pushed set, goal delta
+  uint4* s_cst = s_mail + kOccBlock;                      // per environment: n, g, descriptor word offset, -
+  const uint64_t** s_ft = reinterpret_cast<const uint64_t**>(s_cst + kOccBlock);  // its collision tables
+  const uint64_t** s_tb = s_ft + kOccBlock;                                       // its blob (goal positions)
+  uint16_t* s_list = reinterpret_cast<uint16_t*>(s_tb + kOccBlock);               // [2][kOccBlock] posted environments
   if (threadIdx.x < 4) s_counters[threadIdx.x] = 0;
+  if (threadIdx.x < 2) s_posted[threadIdx.x] = 0;
   if (!kPacked) {
     // record byte -> reward (gym_env.py:212-221): 10 if terminated else (double)dg - 0.01, rounded
     // to float32 once; IEEE arithmetic, so identical to the host-side table of the other kernels
@@ -952,6 +976,11 @@ __global__ void __launch_bounds__(kOccBlock)
       h0 = desc_h(d0);
       agent_rows = 0xffffffffu >> (32 - min(h0, 32));
       agent_cols = 0xffffffffu >> (32 - min(w0, 32));
+      if (kCta) {
+        s_cst[tid] = make_uint4((uint32_t)n, (uint32_t)g, (uint32_t)env.desc_word_, 0u);
+        s_ft[tid] = env.ft.base;
+        s_tb[tid] = env.t.base;
+      }
     };
     auto setup_state = [&]() {  // expects plain positions in env.sm
       const int W = env.width(), H = env.height();
@@ -1029,6 +1058,7 @@ __global__ void __launch_bounds__(kOccBlock)
     uint32_t n_term = 0, n_moved = 0, n_gain = 0, n_invalid = 0;
     constexpr uint32_t kDxBytes = 0x000001ffu, kDyBytes = 0x01ff0000u;  // LEFT, RIGHT, UP, DOWN (puzzle.py:43-50)
     uint32_t all_mask_ok = __ballot_sync(0xffffffffu, mask_ok);
+    uint32_t parity = 0;  // kCta: which of the two posted lists this step fills
     const int blocks = (T + 31) / 32;
     issue_block(0);
     for (int blk = 0; blk < blocks; ++blk) {
@@ -1054,6 +1084,39 @@ __global__ void __launch_bounds__(kOccBlock)
         n_invalid += valid ? 0u : 1u;
         uint32_t pushed = 0u;
         int now = ach;  // goals achieved after this step
+        bool posted = false;
+        if (kCta) {
+          // ---- phase A: the agent's prefilter; environments with a candidate are posted ------------
+          if (mask_ok && go) {
+            const int x = ax + dx, y = ay + dy;
+            const bool framed = (uint32_t)x <= 32u - (uint32_t)min(w0, 32) && (uint32_t)y <= 32u - (uint32_t)min(h0, 32);
+            const uint32_t prows = framed ? agent_rows << y : 0xffffffffu;
+            const uint32_t pcols = framed ? agent_cols << x : 0xffffffffu;
+            uint32_t cand = 0u;
+#pragma unroll 4
+            for (int j = 1; j < n; ++j) {
+              const uint2 v = env.sm[(j - 1) * kOccBlock];
+              const bool near = (v.x & prows) != 0u && (v.y & pcols) != 0u;
+              cand = (cand >> 1) | (near ? 0x80000000u : 0u);
+            }
+            cand = n > 1 ? cand >> (32 - n) : 0u;
+            if (cand == 0u) {  // nothing in the way: the agent moves alone
+              pushed = 1u;
+              ax += dx;
+              ay += dy;
+            } else {
+              posted = true;
+              s_mail[tid] = make_uint4(cand, a, (uint32_t)ax, (uint32_t)ay);
+            }
+          }
+          const uint32_t votes = __ballot_sync(0xffffffffu, posted);
+          if (votes != 0u) {
+            uint32_t first = 0;
+            if (lane == 0) first = atomicAdd(&s_posted[parity], (uint32_t)__popc(votes));
+            first = __shfl_sync(0xffffffffu, first, 0);
+            if (posted) s_list[parity * kOccBlock + first + __popc(votes & ((1u << lane) - 1u))] = (uint16_t)tid;
+          }
+        } else
         if (all_mask_ok != 0u) {
           // ---- mask layout: prefilter + exact look-ups, lanes converged ------------------------
           const bool mine_masks = mask_ok && go;
@@ -1143,6 +1206,83 @@ __global__ void __launch_bounds__(kOccBlock)
           }
           __syncwarp();
         }
+        if (kCta) {
+          __syncthreads();
+          // ---- phase B: one posted environment per thread, resolved completely --------------------
+          if ((uint32_t)tid < s_posted[parity]) {
+            const int q = s_list[parity * kOccBlock + tid];
+            const uint4 mb = s_mail[q];
+            const uint4 cst = s_cst[q];
+            const FastView fv{s_ft[q]};
+            uint2* const sm = s_obj + q;
+            const int qn = (int)cst.x, qg = (int)cst.y;
+            const uint32_t qa = mb.y, qnn1 = 1u + (uint32_t)(qn * qn);
+            const int qdx = action_dx((int)qa), qdy = action_dy((int)qa);
+            uint32_t cand = mb.x, set = 1u, frontier = 0u;
+            int i = 0, xi = (int)mb.z, yi = (int)mb.w;
+            bool stop = false;
+            while (true) {
+              while (cand != 0u) {  // exact look-ups of pusher i's candidates (puzzle.py:567-593, 376-379)
+                const int j = __ffs((int)cand) - 1;
+                cand &= cand - 1;
+                const uint2 v = sm[(j - 1) * kOccBlock];
+                const int xj = __ffs((int)v.y) - 1, yj = __ffs((int)v.x) - 1;
+                if (tab_pushes(fv, 1u + (uint32_t)(i * qn + j), qa, xj - xi, yj - yi)) {
+                  if (tab_wall(fv, qnn1, (uint32_t)j, qa, xj, yj)) {
+                    stop = true;
+                    break;
+                  }
+                  set |= 1u << j;
+                  frontier |= 1u << j;
+                }
+              }
+              if (stop || frontier == 0u) break;
+              i = __ffs((int)frontier) - 1;
+              frontier &= frontier - 1;
+              const uint2 vi = sm[(i - 1) * kOccBlock];
+              xi = __ffs((int)vi.y) - 1;
+              yi = __ffs((int)vi.x) - 1;
+              const uint32_t prows = shift_mask(vi.x, qdy), pcols = shift_mask(vi.y, qdx);
+              for (int j = 1; j < qn; ++j) {
+                const uint2 v = sm[(j - 1) * kOccBlock];
+                const bool near = (v.x & prows) != 0u && (v.y & pcols) != 0u;
+                cand = (cand >> 1) | (near ? 0x80000000u : 0u);
+              }
+              cand = (cand >> (32 - qn)) & ~set;
+            }
+            if (stop) set = 0u;
+            int delta = 0;
+            uint32_t rest = set & ~1u;
+            while (rest != 0u) {  // displace the pushed objects; goal objects among them change the achieved count
+              const int j = __ffs((int)rest) - 1;
+              rest &= rest - 1;
+              const uint2 v = sm[(j - 1) * kOccBlock];
+              const uint2 w = make_uint2(shift_mask(v.x, qdy), shift_mask(v.y, qdx));
+              sm[(j - 1) * kOccBlock] = w;
+              if (j <= qg) {
+                const uint32_t gw = __ldg(reinterpret_cast<const uint32_t*>(s_tb[q]) + cst.z + 4u * (uint32_t)j + 2u);
+                const int gx = lo16(gw), gy = hi16(gw);
+                const bool was = __ffs((int)v.y) - 1 == gx && __ffs((int)v.x) - 1 == gy;
+                const bool is = __ffs((int)w.y) - 1 == gx && __ffs((int)w.x) - 1 == gy;
+                delta += (is ? 1 : 0) - (was ? 1 : 0);
+              }
+            }
+            s_mail[q] = make_uint4(set, (uint32_t)delta, 0u, 0u);
+          }
+          __syncthreads();
+          // ---- phase C: the owners take the verdicts ------------------------------------------------
+          if (tid == 0) s_posted[parity] = 0u;  // consumed; counted again two steps from now, after the next barrier
+          parity ^= 1u;
+          if (posted) {
+            const uint4 res = s_mail[tid];
+            pushed = res.x;
+            if (pushed != 0u) {
+              ax += dx;
+              ay += dy;
+            }
+            now += (int)res.y;
+          }
+        }
         uint32_t code = code_idle;
         n_moved += pushed ? 1u : 0u;
         if (now != ach) {  // (a goal object moved onto / off its goal: rare)
@@ -1202,9 +1342,10 @@ __global__ void __launch_bounds__(kOccBlock)
   flush_counts(c, p, s_counters);
 }
 
-size_t mask_smem_bytes(int n_max) {
+size_t mask_smem_bytes(int n_max, bool cta) {
   const int pos_rows = n_max > 1 ? n_max - 1 : 1;
-  return (size_t)pos_rows * kOccBlock * sizeof(uint2) + (size_t)(kOccBlock / 32) * 2 * kTileBytes + 256 * sizeof(float);
+  return (size_t)pos_rows * kOccBlock * sizeof(uint2) + (size_t)(kOccBlock / 32) * 2 * kTileBytes + 256 * sizeof(float) +
+         (cta ? (size_t)kOccBlock * (2 * sizeof(uint4) + 2 * sizeof(uint64_t*) + 2 * sizeof(uint16_t)) : 0);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1361,15 +1502,24 @@ cudaError_t launch_rollout_occ(const StepParams& p_in, cudaStream_t stream) {
   // PW_OCC_MODE=mask | lockstep | runahead: which general-rule kernel runs (A/B measurements)
   const char* mode = getenv("PW_OCC_MODE");
   if (mode == nullptr || mode[0] == 'm') {
-    const size_t smem = mask_smem_bytes(p.n_max);
+    // PW_MASK_CTA=1 (whole CTAs only): the closure resolved by the CTA, two barriers per step -- measured,
+    // 0.65x of the per-warp lock-step loop, so it is not the default
+    const bool cta = p.N % kOccBlock == 0 && getenv("PW_MASK_CTA") != nullptr;
+    const size_t smem = mask_smem_bytes(p.n_max, cta);
     const bool episodes = (p.flags & kFlagAutoreset) != 0u;
+#define PW_MASK_GO(PACKED, EPISODES)                                                      \
+  do {                                                                                    \
+    if (cta) k_rollout_mask<PACKED, EPISODES, true><<<grid, kOccBlock, smem, stream>>>(p); \
+    else k_rollout_mask<PACKED, EPISODES, false><<<grid, kOccBlock, smem, stream>>>(p);    \
+  } while (0)
     if (p.record) {
-      if (episodes) k_rollout_mask<true, true><<<grid, kOccBlock, smem, stream>>>(p);
-      else k_rollout_mask<true, false><<<grid, kOccBlock, smem, stream>>>(p);
+      if (episodes) PW_MASK_GO(true, true);
+      else PW_MASK_GO(true, false);
     } else {
-      if (episodes) k_rollout_mask<false, true><<<grid, kOccBlock, smem, stream>>>(p);
-      else k_rollout_mask<false, false><<<grid, kOccBlock, smem, stream>>>(p);
+      if (episodes) PW_MASK_GO(false, true);
+      else PW_MASK_GO(false, false);
     }
+#undef PW_MASK_GO
     return cudaGetLastError();
   }
   if (mode[0] == 'l') {
@@ -1398,10 +1548,14 @@ cudaError_t configure_occ_kernels() {
   PW_OPT_IN(k_rollout_occ<false>);
   PW_OPT_IN(k_rollout_occ_ra<true>);
   PW_OPT_IN(k_rollout_occ_ra<false>);
-  PW_OPT_IN((k_rollout_mask<true, true>));
-  PW_OPT_IN((k_rollout_mask<true, false>));
-  PW_OPT_IN((k_rollout_mask<false, true>));
-  PW_OPT_IN((k_rollout_mask<false, false>));
+  PW_OPT_IN((k_rollout_mask<true, true, false>));
+  PW_OPT_IN((k_rollout_mask<true, false, false>));
+  PW_OPT_IN((k_rollout_mask<false, true, false>));
+  PW_OPT_IN((k_rollout_mask<false, false, false>));
+  PW_OPT_IN((k_rollout_mask<true, true, true>));
+  PW_OPT_IN((k_rollout_mask<true, false, true>));
+  PW_OPT_IN((k_rollout_mask<false, true, true>));
+  PW_OPT_IN((k_rollout_mask<false, false, true>));
 #undef PW_OPT_IN
   return err;
 }
