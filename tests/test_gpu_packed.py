@@ -128,3 +128,31 @@ def test_packed_equals_plain_board_mixed_and_episodes(n):
     for a, b in zip(*res):
         assert torch.equal(a, b)
     assert bool(res[0][6].any()) and int(res[0][3].max()) >= 6
+
+
+def test_mask_kernel_with_cta_wide_closure_equals_lock_step():
+    """PW_MASK_CTA=1 (a measured alternative of the general-rule kernel, DESIGN.md 3.5: prefilter
+    candidates of a whole CTA resolved by its first threads between two barriers) against the default
+    lock-step loop: plain and packed outputs, grouped and interleaved puzzle ids, episodes."""
+    import os
+
+    from pushworld_b200 import data
+    from pushworld_b200.engine import Engine
+
+    keys = data.benchmark_keys()
+    engine = Engine([data.puzzle_text(k) for k in keys])
+    n = 4096
+    pid = (torch.arange(n, device="cuda") % len(keys)).to(torch.int32)
+    grouped = torch.sort(pid.long(), stable=True).values.to(torch.int32)
+    cases = [(pid, 96, 41, {}), (grouped, 96, 42, {}),
+             (grouped, 96, 43, dict(max_steps=30, autoreset=True, use_steps=True))]
+    assert "PW_MASK_CTA" not in os.environ
+    base = [_both(engine, ids, n, T, seed, **kw) for ids, T, seed, kw in cases]
+    os.environ["PW_MASK_CTA"] = "1"
+    try:
+        alt = [_both(engine, ids, n, T, seed, **kw) for ids, T, seed, kw in cases]
+    finally:
+        del os.environ["PW_MASK_CTA"]
+    for a, b in zip(base, alt):
+        for x, y in zip(a, b):
+            assert (x is None and y is None) or torch.equal(x, y)

@@ -57,7 +57,8 @@ def main():
     term = torch.empty((T, n), dtype=torch.uint8, device=dev)
     xy = eng.new_state(n)
     results = []
-    variants = [("bounding-box mask prefilter, lock-step (k_rollout_mask)", {})]
+    variants = [("bounding-box mask prefilter, lock-step (k_rollout_mask)", {}),
+                ("mask prefilter, closure work compacted across the CTA, two barriers per step", {"PW_MASK_CTA": "1"})]
     variants += [("occupancy reject, run-ahead lanes, batched closure (k_rollout_occ_ra) batch=%d" % b,
                   {"PW_OCC_MODE": "runahead", "PW_OCC_BATCH": str(b)}) for b in (8,)]
     variants += [("occupancy reject, lock-step, per-thread closure (k_rollout_occ)", {"PW_OCC_MODE": "lockstep"}),
@@ -68,7 +69,7 @@ def main():
     for layout, pid in layouts.items():
         ref = None
         for name, env in variants:
-            for k in ("PW_OCC_WARP_CLOSURE", "PW_OCC_MODE", "PW_OCC_BATCH", "PW_NO_OCC", "PW_WARP_PER_ENV"):
+            for k in ("PW_OCC_WARP_CLOSURE", "PW_OCC_MODE", "PW_OCC_BATCH", "PW_NO_OCC", "PW_WARP_PER_ENV", "PW_MASK_CTA"):
                 os.environ.pop(k, None)
             os.environ.update(env)
 
@@ -86,7 +87,7 @@ def main():
                    "equal_to_first_variant": bool(same), "digest": digest}
             print(json.dumps(rec), flush=True)
             results.append(rec)
-    for k in ("PW_OCC_WARP_CLOSURE", "PW_OCC_MODE", "PW_OCC_BATCH", "PW_NO_OCC", "PW_WARP_PER_ENV"):
+    for k in ("PW_OCC_WARP_CLOSURE", "PW_OCC_MODE", "PW_OCC_BATCH", "PW_NO_OCC", "PW_WARP_PER_ENV", "PW_MASK_CTA"):
         os.environ.pop(k, None)
     if args.out:
         os.makedirs(os.path.dirname(os.path.abspath(args.out)), exist_ok=True)
