@@ -18,7 +18,9 @@
 #include <stdint.h>
 
 #include <cstdlib>
+#include <mutex>
 #include <type_traits>
+#include <vector>
 
 #include "pw_env.cuh"
 #include "pw_fast.cuh"
@@ -843,7 +845,7 @@ size_t table_smem_bytes(int n_states, int block, int kind = 0) {
 // resident CTAs (occupancy API: registers + shared memory) waste the least of the last wave while
 // keeping enough warps to cover the shared-memory latency.
 template <class Kernel>
-int pick_table_block(Kernel kernel, int64_t n_envs, int n_states, int max_block, int kind = 0) {
+int pick_table_block_uncached(Kernel kernel, int64_t n_envs, int n_states, int max_block, int kind) {
   int device = 0, sms = 148;
   cudaGetDevice(&device);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
@@ -871,6 +873,30 @@ int pick_table_block(Kernel kernel, int64_t n_envs, int n_states, int max_block,
     }
   }
   return best_block;
+}
+
+
+// The choice depends on (kernel, batch size, table size) only: remembered, so that the chunked launches of the
+// host pipeline do not pay ~30 occupancy queries each.
+template <class Kernel>
+int pick_table_block(Kernel kernel, int64_t n_envs, int n_states, int max_block, int kind = 0) {
+  struct Entry {
+    const void* kernel;
+    int64_t n_envs;
+    int n_states, block;
+  };
+  static std::mutex mutex;
+  static std::vector<Entry> cache;
+  const void* key = reinterpret_cast<const void*>(kernel);
+  {
+    std::lock_guard<std::mutex> lock(mutex);
+    for (const Entry& e : cache)
+      if (e.kernel == key && e.n_envs == n_envs && e.n_states == n_states) return e.block;
+  }
+  const int block = pick_table_block_uncached(kernel, n_envs, n_states, max_block, kind);
+  std::lock_guard<std::mutex> lock(mutex);
+  if (cache.size() < 256) cache.push_back(Entry{key, n_envs, n_states, block});
+  return block;
 }
 
 }  // namespace
