@@ -150,13 +150,31 @@ struct RegEnv : EnvBase<Table> {
     for (int k = 1; k < NMAX; ++k) v = (i == k) ? d[k] : v;
     return v;
   }
+  // Dynamic index: a chain of selects over the register array -- or, after pack_positions() (callers that
+  // never move the objects: successor expansion), ONE byte permute on a packed copy of the positions.
+  uint32_t xp_[2] = {0u, 0u}, yp_[2] = {0u, 0u};
+  bool packed_ = false;
+  __device__ __forceinline__ void pack_positions() {
+    static_assert(NMAX <= 8, "two words of byte positions");
+    bool ok = true;
+    xp_[0] = xp_[1] = yp_[0] = yp_[1] = 0u;
+#pragma unroll
+    for (int j = 0; j < NMAX; ++j) {
+      ok = ok && (uint32_t)px[j] <= 255u && (uint32_t)py[j] <= 255u;
+      xp_[j >> 2] |= ((uint32_t)px[j] & 0xffu) << (8 * (j & 3));
+      yp_[j >> 2] |= ((uint32_t)py[j] & 0xffu) << (8 * (j & 3));
+    }
+    packed_ = ok;
+  }
   __device__ __forceinline__ int x_dyn(int i) const {
+    if (packed_) return (int)(__byte_perm(xp_[0], xp_[1], (uint32_t)i) & 0xffu);
     int v = px[0];
 #pragma unroll
     for (int k = 1; k < NMAX; ++k) v = (i == k) ? px[k] : v;
     return v;
   }
   __device__ __forceinline__ int y_dyn(int i) const {
+    if (packed_) return (int)(__byte_perm(yp_[0], yp_[1], (uint32_t)i) & 0xffu);
     int v = py[0];
 #pragma unroll
     for (int k = 1; k < NMAX; ++k) v = (i == k) ? py[k] : v;

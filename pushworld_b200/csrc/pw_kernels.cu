@@ -785,6 +785,7 @@ __device__ __forceinline__ void run_expand(Env& env, const ExpandParams& p, int6
   constexpr bool use_agent4 = Env::kStaticN > 0 && Env::kStaticN <= 8;
   uint32_t agent4 = 0;
   if constexpr (use_agent4) {
+    env.pack_positions();  // the state is never modified here: dynamic-index reads become one byte permute
     const int x0 = env.x(0), y0 = env.y(0);
 #pragma unroll
     for (int j = 1; j < Env::kStaticN; ++j) {
@@ -792,22 +793,49 @@ __device__ __forceinline__ void run_expand(Env& env, const ExpandParams& p, int6
       agent4 |= tab_pushes4(env, 1u + (uint32_t)j, env.x(j) - x0, env.y(j) - y0) << (4 * j);
     }
   }
+  // bit 4 j + a of agent4 -> bit j: the nibbles' selected bits gathered by three shift-or-mask rounds
+  auto agent_hits_of = [&](const int a) {
+    uint32_t t = (agent4 >> a) & 0x11111111u;
+    t = (t | (t >> 3)) & 0x03030303u;
+    t = (t | (t >> 6)) & 0x000f000fu;
+    return (t | (t >> 12)) & 0xffu;
+  };
+  // Register policies (n <= 8): the four pushed sets as the four bytes of one word.  An action whose agent
+  // is stopped by a wall, or pushes nothing, is decided at once; the others (a few per cent of the lanes)
+  // are collected and their closures run in ONE loop headed by a warp vote, so that the closure code is
+  // executed max-over-lanes(pending actions) times per warp instead of once per action that any lane
+  // needs it for.
+  uint32_t moved4 = 0;
+  if constexpr (use_agent4) {
+    const uint32_t nn1 = 1u + (uint32_t)(n * n);
+    uint32_t pending = 0;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      if (!tab_wall(env, nn1, 0u, (uint32_t)a, env.x(0), env.y(0))) {  // puzzle.py:353-354
+        if (agent_hits_of(a) == 0u) moved4 |= 1u << (8 * a);
+        else pending |= 1u << a;
+      }
+    }
+    while (__any_sync(live, pending != 0u)) {
+      if (pending != 0u) {
+        const int a = __ffs((int)pending) - 1;
+        pending &= pending - 1;
+        moved4 |= pushed_set_tab(env, a, true, agent_hits_of(a)) << (8 * a);
+      }
+    }
+  }
   auto expand = [&](auto first_offset, auto plane_stride) {
     using Offset = decltype(first_offset);
 #pragma unroll 1
     for (int a = 0; a < 4; ++a) {
-      uint32_t agent_hits = 0;
+      uint32_t moved;
       if constexpr (use_agent4) {
-        // bit 4 j + a of agent4 -> bit j: the nibbles' selected bits gathered by three shift-or-mask rounds
-        uint32_t t = (agent4 >> a) & 0x11111111u;
-        t = (t | (t >> 3)) & 0x03030303u;
-        t = (t | (t >> 6)) & 0x000f000fu;
-        agent_hits = (t | (t >> 12)) & 0xffu;
+        moved = (moved4 >> (8 * a)) & 0xffu;
+      } else {
+        moved = pushed_set_tab(env, a);
+        // the closure's data-dependent loops leave the lanes apart: reconverge before the stores
+        __syncwarp(live);
       }
-      const uint32_t moved = pushed_set_tab(env, a, use_agent4, agent_hits);
-      // the closure's data-dependent loops leave the lanes apart; without this the stores below ran with a
-      // quarter of the lanes (ncu: 8 of 32 active)
-      __syncwarp(live);
       const int dx = moved ? action_dx(a) : 0, dy = moved ? action_dy(a) : 0;
       const Offset s = (Offset)a * (Offset)p.N + first_offset;
       Offset off = s;
