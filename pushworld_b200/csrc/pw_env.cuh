@@ -122,6 +122,18 @@ struct RegEnv : EnvBase<Table> {
         py[j] = y[j * stride + e];
       }
   }
+  // the same with 32-bit element offsets (planes of fewer than 2^31 elements): one IMAD.WIDE per address
+  __device__ __forceinline__ void load32(const int32_t* x, const int32_t* y, uint32_t stride, uint32_t e) {
+    uint32_t off = e;
+#pragma unroll
+    for (int j = 0; j < NMAX; ++j) {
+      if (j < this->n_) {
+        px[j] = x[off];
+        py[j] = y[off];
+      }
+      off += stride;
+    }
+  }
   __device__ __forceinline__ void load_initial() {
 #pragma unroll
     for (int j = 0; j < NMAX; ++j)
@@ -210,6 +222,13 @@ struct SmemEnv : EnvBase<Table> {
     for (int j = 0; j < this->n_; ++j) {
       sx[j * pitch] = x[j * stride + e];
       sy[j * pitch] = y[j * stride + e];
+    }
+  }
+  __device__ __forceinline__ void load32(const int32_t* x, const int32_t* y, uint32_t stride, uint32_t e) {
+    uint32_t off = e;
+    for (int j = 0; j < this->n_; ++j, off += stride) {
+      sx[j * pitch] = x[off];
+      sy[j * pitch] = y[off];
     }
   }
   __device__ __forceinline__ void load_initial() {

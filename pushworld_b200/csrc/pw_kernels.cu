@@ -772,7 +772,11 @@ __global__ void __launch_bounds__(kBlock)
 template <class Env>
 __device__ __forceinline__ void run_expand(Env& env, const ExpandParams& p, int64_t e) {
   const unsigned live = __activemask();  // the warp's lanes that have a state (converged here)
-  env.load(p.x_in, p.y_in, p.stride_in, p.index ? p.index[e] : e);
+  {
+    const int64_t src = p.index ? p.index[e] : e;
+    if (p.stride_in * (int64_t)p.n_max < ((int64_t)1 << 31)) env.load32(p.x_in, p.y_in, (uint32_t)p.stride_in, (uint32_t)src);
+    else env.load(p.x_in, p.y_in, p.stride_in, src);
+  }
   const int g = env.g(), n = env.n();
   const int jend = Env::kStaticN ? Env::kStaticN : n;
   // The state itself is never modified: successor a is the state with the pushed set displaced,
