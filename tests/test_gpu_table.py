@@ -165,3 +165,26 @@ def test_every_table_kernel_variant(variant, n, T):
             os.environ.pop(k, None)
             if saved[k] is not None:
                 os.environ[k] = saved[k]
+
+
+def test_every_benchmark_puzzle_with_and_without_tables():
+    """All 223 benchmark puzzles, one engine each: whatever the engine tabulates (13 puzzles have few enough
+    reachable states; one-goal ones get the two-step table, the others the one-step form) must roll out
+    exactly like the engine without tables -- states numbered terminal-last, several goals, tall grids."""
+    from pushworld_b200 import data
+
+    n, T = 256, 48
+    gen = torch.Generator(device="cuda").manual_seed(77)
+    actions = torch.randint(0, 4, (T, n), dtype=torch.uint8, device="cuda", generator=gen)
+    warm = torch.randint(0, 4, (24, n), dtype=torch.uint8, device="cuda", generator=gen)
+    for key in data.benchmark_keys():
+        text = data.puzzle_text(key)
+        tab, ref = _engine(text, True), _engine(text, False)
+        xy0 = tab.new_state(n)
+        tab.reset(xy0, 0)
+        ref.rollout(xy0, 0, warm)  # spread the environments out with the general rule
+        base = _run(ref, xy0, actions, False)
+        for packed in (False, True):
+            got = _run(tab, xy0, actions, packed)
+            for a, b in zip(got, base):
+                assert torch.equal(a, b), (key, packed)
