@@ -42,7 +42,13 @@ for label, env in (("mask kernel (k_rollout_mask)", {}), ("scan every step (roun
     def episodes():
         eng.rollout_episodes(xy, pid, actions, steps, episode, seed=11, max_steps=100, reward=reward, terminated=term, truncated=trunc)
     ms_e = time_ms(episodes)
+    def episodes_long():  # no truncation inside the rollout: only solved puzzles restart
+        eng.rollout_episodes(xy, pid, actions, steps, episode, seed=11, max_steps=10**6, reward=reward, terminated=term, truncated=trunc)
+    eng.reset(xy, pid, steps=steps)
+    ms_l = time_ms(episodes_long)
+    n_restarts = int(episode.sum())
     res[label] = dig
     print(json.dumps({"path": label, "plain_ms": round(ms, 3), "plain_steps_per_s": n*T/ms*1e3, "episodes_ms": round(ms_e, 3),
-                      "episodes_steps_per_s": n*T/ms_e*1e3, "digest": dig}), flush=True)
+                      "episodes_steps_per_s": n*T/ms_e*1e3, "episodes_no_truncation_ms": round(ms_l, 3),
+                      "restarts_seen_no_truncation": n_restarts, "digest": dig}), flush=True)
 print("plain rollouts equal:", len(set(res.values())) == 1)
