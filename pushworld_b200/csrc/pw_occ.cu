@@ -1058,6 +1058,7 @@ __global__ void __launch_bounds__(kOccBlock)
     uint32_t n_term = 0, n_moved = 0, n_gain = 0, n_invalid = 0;
     constexpr uint32_t kDxBytes = 0x000001ffu, kDyBytes = 0x01ff0000u;  // LEFT, RIGHT, UP, DOWN (puzzle.py:43-50)
     uint32_t all_mask_ok = __ballot_sync(0xffffffffu, mask_ok);
+    int n_warp = __reduce_max_sync(0xffffffffu, n);  // the warp's largest object count
     uint32_t parity = 0;  // kCta: which of the two posted lists this step fills
     const int blocks = (T + 31) / 32;
     issue_block(0);
@@ -1142,15 +1143,18 @@ __global__ void __launch_bounds__(kOccBlock)
               prows = shift_mask(v.x, dy);
               pcols = shift_mask(v.y, dx);
             }
+            // the trip count is the warp's largest object count (lanes with fewer objects, and lanes without
+            // a pusher, test nothing): a uniform loop instead of one whose bound differs per lane
             uint32_t cand = 0u;
-            if (active) {
+            {
+              const int mine_n = active ? n : 0;
 #pragma unroll 4
-              for (int j = 1; j < n; ++j) {
+              for (int j = 1; j < n_warp; ++j) {
                 const uint2 v = env.sm[(j - 1) * kOccBlock];
-                const bool near = (v.x & prows) != 0u && (v.y & pcols) != 0u;
+                const bool near = j < mine_n && (v.x & prows) != 0u && (v.y & pcols) != 0u;
                 cand = (cand >> 1) | (near ? 0x80000000u : 0u);
               }
-              cand = n > 1 ? cand >> (32 - n) : 0u;
+              cand = n_warp > 1 ? cand >> (32 - n_warp) : 0u;
               cand &= ~pushed;
             }
             while (__any_sync(0xffffffffu, cand != 0u)) {
@@ -1328,6 +1332,7 @@ __global__ void __launch_bounds__(kOccBlock)
             ep_steps = 0;
           }
           all_mask_ok = __ballot_sync(0xffffffffu, mask_ok);
+          n_warp = __reduce_max_sync(0xffffffffu, n);
         }
       }
     }
