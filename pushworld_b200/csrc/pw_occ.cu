@@ -831,11 +831,16 @@ __global__ void __launch_bounds__(kOccBlock)
 // Environments that do not qualify (bigger grid, a movable outside the grid or on a wall) keep
 // plain positions and run pushed_set_tab, the round-1 rule, in the same loop.
 // ------------------------------------------------------------------------------------------
+// Row pitch of the per-object mask rows in shared memory, in uint2: one more than the CTA size, so that the
+// lanes of a warp reading ONE environment's objects (the cooperative prefilter below) hit different banks.
+constexpr int kMaskPitch = kOccBlock + 1;
+constexpr int kCoopCost = 3;  // a cooperative prefilter pass costs about as much as three objects of the per-lane loop
+
 struct MaskEnv : EnvBase<GlobalTable> {
   static constexpr int kStaticN = 0;
   static constexpr int kUnroll = 1;
   int ax, ay;
-  uint2* sm;  // object j >= 1 at sm[(j - 1) * kOccBlock]: masks (x = rows, y = columns) or plain (x, y)
+  uint2* sm;  // object j >= 1 at sm[(j - 1) * kMaskPitch]: masks (x = rows, y = columns) or plain (x, y)
   bool masks = false;
   __device__ __forceinline__ void init(GlobalTable table, uint2* col) {
     this->init_header(table);
@@ -845,7 +850,7 @@ struct MaskEnv : EnvBase<GlobalTable> {
     ax = x[e];
     ay = y[e];
     for (int j = 1; j < this->n_; ++j)
-      sm[(j - 1) * kOccBlock] = make_uint2((uint32_t)x[j * stride + e], (uint32_t)y[j * stride + e]);
+      sm[(j - 1) * kMaskPitch] = make_uint2((uint32_t)x[j * stride + e], (uint32_t)y[j * stride + e]);
   }
   __device__ __forceinline__ void store(int32_t* x, int32_t* y, int64_t stride, int64_t e) const {
     x[e] = ax;
@@ -862,7 +867,7 @@ struct MaskEnv : EnvBase<GlobalTable> {
     ay = hi16(v0);
     for (int j = 1; j < this->n_; ++j) {
       const uint32_t v = this->table_desc(j, 1);
-      sm[(j - 1) * kOccBlock] = make_uint2((uint32_t)lo16(v), (uint32_t)hi16(v));
+      sm[(j - 1) * kMaskPitch] = make_uint2((uint32_t)lo16(v), (uint32_t)hi16(v));
     }
   }
   __device__ __forceinline__ uint32_t desc(int j) const { return this->table_desc(j, 0); }
@@ -870,12 +875,12 @@ struct MaskEnv : EnvBase<GlobalTable> {
   // plain layout: (x, y); mask layout: (row mask, column mask)
   __device__ __forceinline__ int x(int j) const {
     if (j == 0) return ax;
-    const uint2 v = sm[(j - 1) * kOccBlock];
+    const uint2 v = sm[(j - 1) * kMaskPitch];
     return masks ? __ffs((int)v.y) - 1 : (int)v.x;
   }
   __device__ __forceinline__ int y(int j) const {
     if (j == 0) return ay;
-    const uint2 v = sm[(j - 1) * kOccBlock];
+    const uint2 v = sm[(j - 1) * kMaskPitch];
     return masks ? __ffs((int)v.x) - 1 : (int)v.y;
   }
   __device__ __forceinline__ int x_dyn(int j) const { return x(j); }
@@ -891,10 +896,10 @@ struct MaskEnv : EnvBase<GlobalTable> {
     while (mask) {
       const int j = __ffs((int)mask) - 1;
       mask &= mask - 1;
-      uint2 v = sm[(j - 1) * kOccBlock];
+      uint2 v = sm[(j - 1) * kMaskPitch];
       v.x += (uint32_t)dx;
       v.y += (uint32_t)dy;
-      sm[(j - 1) * kOccBlock] = v;
+      sm[(j - 1) * kMaskPitch] = v;
     }
   }
 };
@@ -930,7 +935,7 @@ __global__ void __launch_bounds__(kOccBlock)
   // dynamic shared memory: object masks / positions | action tiles | reward table | kCta: mail boxes, lists
   uint2* s_obj = reinterpret_cast<uint2*>(smem_raw);
   const int pos_rows = p.n_max > 1 ? p.n_max - 1 : 1;
-  uint8_t* s_act = reinterpret_cast<uint8_t*>(s_obj + pos_rows * kOccBlock);
+  uint8_t* s_act = smem_raw + (((size_t)pos_rows * kMaskPitch * sizeof(uint2) + 15) & ~(size_t)15);
   float* s_lut = reinterpret_cast<float*>(s_act + (kOccBlock / 32) * 2 * kTileBytes);
   uint4* s_mail = reinterpret_cast<uint4*>(s_lut + 256);  // in: candidates, action, ax, ay; out: pushed set, goal delta
   uint4* s_cst = s_mail + kOccBlock;                      // per environment: n, g, descriptor word offset, -
@@ -1004,8 +1009,8 @@ __global__ void __launch_bounds__(kOccBlock)
       if (mask_ok) {
         for (int j = 1; j < n; ++j) {
           const uint32_t d = env.desc(j);
-          const uint2 v = env.sm[(j - 1) * kOccBlock];
-          env.sm[(j - 1) * kOccBlock] = make_uint2((0xffffffffu >> (32 - desc_h(d))) << v.y,
+          const uint2 v = env.sm[(j - 1) * kMaskPitch];
+          env.sm[(j - 1) * kMaskPitch] = make_uint2((0xffffffffu >> (32 - desc_h(d))) << v.y,
                                                    (0xffffffffu >> (32 - desc_w(d))) << v.x);
         }
         env.masks = true;
@@ -1023,7 +1028,7 @@ __global__ void __launch_bounds__(kOccBlock)
         env.ay = hi16(v0);
         for (int j = 1; j < n; ++j) {
           const uint64_t m = env.fast(section + (uint32_t)j);
-          env.sm[(j - 1) * kOccBlock] = make_uint2((uint32_t)m, (uint32_t)(m >> 32));
+          env.sm[(j - 1) * kMaskPitch] = make_uint2((uint32_t)m, (uint32_t)(m >> 32));
         }
         env.masks = true;
         mask_ok = true;
@@ -1096,7 +1101,7 @@ __global__ void __launch_bounds__(kOccBlock)
             uint32_t cand = 0u;
 #pragma unroll 4
             for (int j = 1; j < n; ++j) {
-              const uint2 v = env.sm[(j - 1) * kOccBlock];
+              const uint2 v = env.sm[(j - 1) * kMaskPitch];
               const bool near = (v.x & prows) != 0u && (v.y & pcols) != 0u;
               cand = (cand >> 1) | (near ? 0x80000000u : 0u);
             }
@@ -1137,7 +1142,7 @@ __global__ void __launch_bounds__(kOccBlock)
               prows = framed ? agent_rows << y : 0xffffffffu;
               pcols = framed ? agent_cols << x : 0xffffffffu;
             } else {
-              const uint2 v = env.sm[(i - 1) * kOccBlock];
+              const uint2 v = env.sm[(i - 1) * kMaskPitch];
               xi = __ffs((int)v.y) - 1;
               yi = __ffs((int)v.x) - 1;
               prows = shift_mask(v.x, dy);
@@ -1146,22 +1151,41 @@ __global__ void __launch_bounds__(kOccBlock)
             // the trip count is the warp's largest object count (lanes with fewer objects, and lanes without
             // a pusher, test nothing): a uniform loop instead of one whose bound differs per lane
             uint32_t cand = 0u;
-            {
+            uint32_t pushers = __ballot_sync(0xffffffffu, active);
+            if (__popc(pushers) * kCoopCost >= n_warp) {
               const int mine_n = active ? n : 0;
 #pragma unroll 4
               for (int j = 1; j < n_warp; ++j) {
-                const uint2 v = env.sm[(j - 1) * kOccBlock];
+                const uint2 v = env.sm[(j - 1) * kMaskPitch];
                 const bool near = j < mine_n && (v.x & prows) != 0u && (v.y & pcols) != 0u;
                 cand = (cand >> 1) | (near ? 0x80000000u : 0u);
               }
               cand = n_warp > 1 ? cand >> (32 - n_warp) : 0u;
               cand &= ~pushed;
+            } else {
+              // Later closure rounds have a pusher in one or two lanes only: instead of every lane walking the
+              // loop above for them, the WARP tests one such environment's objects in parallel -- lane L takes
+              // object L of environment q (its masks are in shared memory; the row pitch keeps the 32 reads on
+              // different banks) -- and the ballot is q's candidate set.
+              while (pushers != 0u) {
+                const int q = __ffs((int)pushers) - 1;
+                pushers &= pushers - 1;
+                const uint32_t q_rows = __shfl_sync(0xffffffffu, prows, q), q_cols = __shfl_sync(0xffffffffu, pcols, q);
+                const int q_n = __shfl_sync(0xffffffffu, n, q);
+                bool near = false;
+                if (lane >= 1u && (int)lane < q_n) {
+                  const uint2 v = env.sm[((int)lane - 1) * kMaskPitch + (q - (int)lane)];
+                  near = (v.x & q_rows) != 0u && (v.y & q_cols) != 0u;
+                }
+                const uint32_t found = __ballot_sync(0xffffffffu, near);
+                if ((int)lane == q) cand = found & ~pushed;
+              }
             }
             while (__any_sync(0xffffffffu, cand != 0u)) {
               if (cand != 0u) {
                 const int j = __ffs((int)cand) - 1;
                 cand &= cand - 1;
-                const uint2 v = env.sm[(j - 1) * kOccBlock];
+                const uint2 v = env.sm[(j - 1) * kMaskPitch];
                 const int xj = __ffs((int)v.y) - 1, yj = __ffs((int)v.x) - 1;
                 if (tab_pushes(env, 1u + (uint32_t)(i * n + j), a, xj - xi, yj - yi)) {
                   if (tab_wall(env, nn1, (uint32_t)j, a, xj, yj)) {  // transitive stopping, puzzle.py:376-379
@@ -1188,9 +1212,9 @@ __global__ void __launch_bounds__(kOccBlock)
             if (rest != 0u) {
               const int j = __ffs((int)rest) - 1;
               rest &= rest - 1;
-              const uint2 v = env.sm[(j - 1) * kOccBlock];
+              const uint2 v = env.sm[(j - 1) * kMaskPitch];
               const uint2 w = make_uint2(shift_mask(v.x, dy), shift_mask(v.y, dx));
-              env.sm[(j - 1) * kOccBlock] = w;
+              env.sm[(j - 1) * kMaskPitch] = w;
               if (j <= g) {
                 const uint32_t gw = env.table_desc(j, 2);
                 const int gx = lo16(gw), gy = hi16(gw);
@@ -1229,7 +1253,7 @@ __global__ void __launch_bounds__(kOccBlock)
               while (cand != 0u) {  // exact look-ups of pusher i's candidates (puzzle.py:567-593, 376-379)
                 const int j = __ffs((int)cand) - 1;
                 cand &= cand - 1;
-                const uint2 v = sm[(j - 1) * kOccBlock];
+                const uint2 v = sm[(j - 1) * kMaskPitch];
                 const int xj = __ffs((int)v.y) - 1, yj = __ffs((int)v.x) - 1;
                 if (tab_pushes(fv, 1u + (uint32_t)(i * qn + j), qa, xj - xi, yj - yi)) {
                   if (tab_wall(fv, qnn1, (uint32_t)j, qa, xj, yj)) {
@@ -1243,12 +1267,12 @@ __global__ void __launch_bounds__(kOccBlock)
               if (stop || frontier == 0u) break;
               i = __ffs((int)frontier) - 1;
               frontier &= frontier - 1;
-              const uint2 vi = sm[(i - 1) * kOccBlock];
+              const uint2 vi = sm[(i - 1) * kMaskPitch];
               xi = __ffs((int)vi.y) - 1;
               yi = __ffs((int)vi.x) - 1;
               const uint32_t prows = shift_mask(vi.x, qdy), pcols = shift_mask(vi.y, qdx);
               for (int j = 1; j < qn; ++j) {
-                const uint2 v = sm[(j - 1) * kOccBlock];
+                const uint2 v = sm[(j - 1) * kMaskPitch];
                 const bool near = (v.x & prows) != 0u && (v.y & pcols) != 0u;
                 cand = (cand >> 1) | (near ? 0x80000000u : 0u);
               }
@@ -1260,9 +1284,9 @@ __global__ void __launch_bounds__(kOccBlock)
             while (rest != 0u) {  // displace the pushed objects; goal objects among them change the achieved count
               const int j = __ffs((int)rest) - 1;
               rest &= rest - 1;
-              const uint2 v = sm[(j - 1) * kOccBlock];
+              const uint2 v = sm[(j - 1) * kMaskPitch];
               const uint2 w = make_uint2(shift_mask(v.x, qdy), shift_mask(v.y, qdx));
-              sm[(j - 1) * kOccBlock] = w;
+              sm[(j - 1) * kMaskPitch] = w;
               if (j <= qg) {
                 const uint32_t gw = __ldg(reinterpret_cast<const uint32_t*>(s_tb[q]) + cst.z + 4u * (uint32_t)j + 2u);
                 const int gx = lo16(gw), gy = hi16(gw);
@@ -1349,7 +1373,8 @@ __global__ void __launch_bounds__(kOccBlock)
 
 size_t mask_smem_bytes(int n_max, bool cta) {
   const int pos_rows = n_max > 1 ? n_max - 1 : 1;
-  return (size_t)pos_rows * kOccBlock * sizeof(uint2) + (size_t)(kOccBlock / 32) * 2 * kTileBytes + 256 * sizeof(float) +
+  return (((size_t)pos_rows * kMaskPitch * sizeof(uint2) + 15) & ~(size_t)15) + (size_t)(kOccBlock / 32) * 2 * kTileBytes +
+         256 * sizeof(float) +
          (cta ? (size_t)kOccBlock * (2 * sizeof(uint4) + 2 * sizeof(uint64_t*) + 2 * sizeof(uint16_t)) : 0);
 }
 
