@@ -1041,6 +1041,12 @@ __global__ void __launch_bounds__(kOccBlock)
     };
     setup_puzzle();
     setup_state();
+    // rows past this environment's last object hold empty masks: the prefilter loop runs to the warp's
+    // largest object count without a per-object bound test
+    auto clear_unused_rows = [&]() {
+      for (int j = n; j <= pos_rows; ++j) env.sm[(j - 1) * kMaskPitch] = make_uint2(0u, 0u);
+    };
+    clear_unused_rows();
     int& ax = env.ax;
     int& ay = env.ay;
     int ep_steps = kEpisodes ? p.steps[e] : 0;
@@ -1153,11 +1159,11 @@ __global__ void __launch_bounds__(kOccBlock)
             uint32_t cand = 0u;
             uint32_t pushers = __ballot_sync(0xffffffffu, active);
             if (__popc(pushers) * kCoopCost >= n_warp) {
-              const int mine_n = active ? n : 0;
+              const uint32_t my_rows = active ? prows : 0u;  // (rows past the lane's own objects are empty masks)
 #pragma unroll 4
               for (int j = 1; j < n_warp; ++j) {
                 const uint2 v = env.sm[(j - 1) * kMaskPitch];
-                const bool near = j < mine_n && (v.x & prows) != 0u && (v.y & pcols) != 0u;
+                const bool near = (v.x & my_rows) != 0u && (v.y & pcols) != 0u;
                 cand = (cand >> 1) | (near ? 0x80000000u : 0u);
               }
               cand = n_warp > 1 ? cand >> (32 - n_warp) : 0u;
@@ -1351,6 +1357,7 @@ __global__ void __launch_bounds__(kOccBlock)
               p.puzzle_id_mut[e] = pid;
               env.retarget(p.blob + p.puzzle_off[pid]);
               setup_puzzle();
+              clear_unused_rows();
             }
             restart_episode();
             ep_steps = 0;
