@@ -473,6 +473,10 @@ def run_ours(args) -> None:
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+    # The only collective is a 32-byte all-reduce per rollout, overlapped with the next rollout, whose 128 CTAs
+    # need 128 of the 148 SMs at once: with NCCL's default channel count its (spinning) CTAs take more than the 20
+    # free SMs and push part of the rollout into a second wave (+0.035 ms per 0.31 ms step at N = 8, measured).
+    os.environ.setdefault("NCCL_MAX_NCHANNELS", "4")
     rank, local_rank, world = distributed.init_from_env("nccl")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -489,18 +493,24 @@ def run_ours(args) -> None:
         counters=torch.zeros(4, dtype=torch.int64, device=dev),
     )
     # The path's single collective: ONE all-reduce (sum) of the int64[4] counter vector PER ROLLOUT.
-    # It runs on a side stream and overlaps the next rollout (counter vectors are double buffered).
+    # It runs on a side stream and overlaps the next rollouts: the counter vectors are a ring of kRing
+    # buffers, so the launching stream only waits for the all-reduce of kRing rollouts ago (with two
+    # buffers an all-reduce that NCCL could not schedule next to the rollout's 128 resident CTAs held
+    # the next-but-one rollout back: 0.05 ms per step at N = 8).
+    kRing = 4
+    # diagnostic only (PW_BENCH_NO_ALLREDUCE=1): one all-reduce at the end instead of one per rollout
+    skip_allreduce = os.environ.get("PW_BENCH_NO_ALLREDUCE") == "1"
     side = torch.cuda.Stream(dev)
-    counters = [torch.zeros(4, dtype=torch.int64, device=dev) for _ in range(2)]
-    reduced = [torch.zeros(4, dtype=torch.int64, device=dev) for _ in range(2)]
+    counters = [torch.zeros(4, dtype=torch.int64, device=dev) for _ in range(kRing)]
+    reduced = [torch.zeros(4, dtype=torch.int64, device=dev) for _ in range(kRing)]
     totals = torch.zeros(4, dtype=torch.int64, device=dev)
-    ev_done = [torch.cuda.Event() for _ in range(2)]
-    ev_free = [torch.cuda.Event() for _ in range(2)]
+    ev_done = [torch.cuda.Event() for _ in range(kRing)]
+    ev_free = [torch.cuda.Event() for _ in range(kRing)]
 
     def one_step(k, ev0=None, ev1=None):
-        b = k & 1
+        b = k % kRing
         cur = torch.cuda.current_stream(dev)
-        cur.wait_event(ev_free[b])  # the all-reduce of rollout k-2 has consumed counters[b]
+        cur.wait_event(ev_free[b])  # the all-reduce of rollout k - kRing has consumed counters[b]
         counters[b].zero_()
         out.counters = counters[b]
         env.reset()
@@ -513,7 +523,8 @@ def run_ours(args) -> None:
         with torch.cuda.stream(side):
             side.wait_event(ev_done[b])
             reduced[b].copy_(counters[b])
-            distributed.allreduce_counters(reduced[b])  # NCCL, int64[4]
+            if not skip_allreduce:
+                distributed.allreduce_counters(reduced[b])  # NCCL, int64[4]
             totals.add_(reduced[b])
             ev_free[b].record(side)
 
@@ -538,6 +549,8 @@ def run_ours(args) -> None:
         one_step(k, *kernel_events[k])
     host_issue_ms = (time.perf_counter() - host_t0) * 1e3 / max(args.steps, 1)  # launch work of one step, host side
     torch.cuda.current_stream(dev).wait_stream(side)  # the last all-reduce is part of the job
+    if skip_allreduce:
+        distributed.allreduce_counters(totals)
     stop.record()
     torch.cuda.synchronize()
     sampler.mark_end()
@@ -548,6 +561,7 @@ def run_ours(args) -> None:
     assert total_env_steps == world * args.steps * N_ENVS * T_STEPS, total_env_steps
     value = total_env_steps / (elapsed_ms * 1e-3)
     kernel_ms = statistics.mean(a.elapsed_time(b) for a, b in kernel_events)
+    kernel_ms_slowest = distributed.max_over_ranks(kernel_ms, dev)  # the GPU that sets the max-over-ranks time
     out.counters = counters[0]
 
     # ---- end to end: pinned host buffers in, pinned host buffers out ---------------------
@@ -629,6 +643,7 @@ def run_ours(args) -> None:
     roofline = {
         "bound": "hbm",
         "kernel": ROLLOUT_KERNEL,
+        "kernel_ms_slowest_rank": kernel_ms_slowest,
         "achieved": achieved,
         "peak": peak,
         "unit": "GB/s",
