@@ -926,10 +926,11 @@ struct FastView {  // the collision tables of a posted environment (what tab_pus
   __device__ __forceinline__ uint32_t fast32(uint32_t k) const { return __ldg(reinterpret_cast<const uint32_t*>(ft) + k); }
 };
 
-// (the episode variants are capped at 72 registers -- 7 CTAs per SM instead of 6 -- which the compiler meets without
-// spills: 3.4e10 -> 4.3e10 env-steps/s on the real level-0 set; a cap of 64 registers spills and loses)
+// (capped at 72 registers -- 7 CTAs per SM; uncapped, the episode variants take 80 and the others up to 91 -- which
+// the compiler meets without spills: 3.4e10 -> 4.4e10 env-steps/s on the real level-0 set; a cap of 64 registers
+// spills in the plain variants and loses a quarter)
 template <bool kPacked, bool kEpisodes, bool kCta>
-__global__ void __launch_bounds__(kOccBlock, kEpisodes ? 7 : 1)
+__global__ void __launch_bounds__(kOccBlock, 7)
     k_rollout_mask(const __grid_constant__ StepParams p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   __shared__ uint32_t s_counters[4];
@@ -1065,9 +1066,9 @@ __global__ void __launch_bounds__(kOccBlock, kEpisodes ? 7 : 1)
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u), "l"(src + 16) : "memory");
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    float* rew = kPacked ? nullptr : p.reward + e;
-    uint8_t* out8 = kPacked ? p.record + e : p.terminated + e;
-    uint8_t* trunc8 = (kEpisodes && !kPacked && p.truncated) ? p.truncated + e : nullptr;
+    // outputs of step t at element offset t * N + e: ONE running 64-bit offset instead of three running pointers
+    int64_t out_off = e;
+    const bool want_trunc = kEpisodes && !kPacked && p.truncated != nullptr;
     uint32_t n_term = 0, n_moved = 0, n_gain = 0, n_invalid = 0;
     constexpr uint32_t kDxBytes = 0x000001ffu, kDyBytes = 0x01ff0000u;  // LEFT, RIGHT, UP, DOWN (puzzle.py:43-50)
     uint32_t all_mask_ok = __ballot_sync(0xffffffffu, mask_ok);
@@ -1337,19 +1338,17 @@ __global__ void __launch_bounds__(kOccBlock, kEpisodes ? 7 : 1)
           restart = (code >> 7) != 0u || trunc;
           if (kPacked) {
             code |= trunc ? 0x40u : 0u;
-          } else if (trunc8) {
-            *trunc8 = trunc ? 1 : 0;
-            trunc8 += p.N;
+          } else if (want_trunc) {
+            p.truncated[out_off] = trunc ? 1 : 0;
           }
         }
         if (kPacked) {
-          *out8 = (uint8_t)code;
+          p.record[out_off] = (uint8_t)code;
         } else {
-          *rew = s_lut[code & 0xbfu];
-          *out8 = (uint8_t)(code >> 7);
-          rew += p.N;
+          p.reward[out_off] = s_lut[code & 0xbfu];
+          p.terminated[out_off] = (uint8_t)(code >> 7);
         }
-        out8 += p.N;
+        out_off += p.N;
         if (kEpisodes && __any_sync(0xffffffffu, restart)) {
           if (restart) {  // gym_env.py:171-176: a new episode, on a freshly drawn puzzle if asked for
             if (p.flags & kFlagResample) {
