@@ -14,6 +14,13 @@
 // Exact by construction: every entry was computed by the same rule every other kernel uses, and an
 // environment whose loaded state is not in the table (not reachable from the initial state) makes
 // its warp run the general rule instead.
+//
+// Kernels, fastest first (launch_rollout_table picks the first that fits the launch):
+//   k_rollout_pairs4  two-step table (state, a1, a2), FOUR environments per thread, packed-byte bookkeeping,
+//                     16-byte reward stores: one-goal puzzles with <= 6,144 states, N % 128 == 0, aligned outputs
+//   k_rollout_pairs   the same table, one environment per thread (any N % 32 == 0, any alignment)
+//   k_rollout_table   one-step table: compact entries (one goal, <= 8,192 states) or the 32-bit entries above
+// DESIGN.md section 3.2c has the measurements that led here (tools/table_probe.py, tools/probes/).
 #include <cuda_runtime.h>
 #include <stdint.h>
 
