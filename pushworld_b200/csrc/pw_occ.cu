@@ -1176,6 +1176,7 @@ __global__ void __launch_bounds__(kOccBlock, 7)
               // loop above for them, the WARP tests one such environment's objects in parallel -- lane L takes
               // object L of environment q (its masks are in shared memory; the row pitch keeps the 32 reads on
               // different banks) -- and the ballot is q's candidate set.
+              __syncwarp();  // the owners' mask writes (displacement, restarts) before other lanes read them
               while (pushers != 0u) {
                 const int q = __ffs((int)pushers) - 1;
                 pushers &= pushers - 1;
@@ -1189,6 +1190,7 @@ __global__ void __launch_bounds__(kOccBlock, 7)
                 const uint32_t found = __ballot_sync(0xffffffffu, near);
                 if ((int)lane == q) cand = found & ~pushed;
               }
+              __syncwarp();  // ... and those reads before the owners write again
             }
             while (__any_sync(0xffffffffu, cand != 0u)) {
               if (cand != 0u) {
